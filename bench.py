@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Headline benchmark: KernelWeighting forward+backward throughput.
+
+Metric (BASELINE.json): Msamples/s, samples = B*spp*H*W per step, one step =
+the reference call pattern for one batch: `spp` calls of KernelWeighting
+forward + backward on data [B,3,H,W] x weights [B,K,K,H,W] (the model calls the
+op once per sample index, sbmc/models.py:195-206 of the reference).
+Default workload = BASELINE.json configs[1]: B=4, spp=8, 1280x720, K=21, fp32.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 (launched by torch.distributed.run, one rank per GPU): the image is cut
+into N row bands (H-sharding); every rank owns a band of
+`--h` rows (weak scaling: the image is N*h rows tall), exchanges the K-1 halo
+rows of `data` (forward) and of `d_data` (backward) with its neighbours over
+NCCL, and the rank-0 line reports the whole-job Msamples/s (max over ranks).
+
+One JSON line is printed by rank 0; see DESIGN.md section "Measurement" for the
+meaning of every key (roofline / cpu_baseline / e2e / clocks / gpu_launches).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/s (spp*H*W) KernelWeighting fwd+bwd"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--b", type=int, default=4)
+    p.add_argument("--spp", type=int, default=8)
+    p.add_argument("--h", type=int, default=720)
+    p.add_argument("--w", type=int, default=1280)
+    p.add_argument("--k", type=int, default=21)
+    p.add_argument("--c", type=int, default=3)
+    p.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--cpu-seconds", type=float, default=12.0,
+                   help="target CPU time of the cpu_baseline sample")
+    return p.parse_args()
+
+
+def workload(a):
+    return {"workload": "KernelWeighting fwd+bwd, B=%d spp=%d %dx%d K=%d C=%d fp32 "
+                        "(BASELINE configs[1]; %d calls of [B,C,H,W]x[B,K,K,H,W] per step)"
+                        % (a.b, a.spp, a.w, a.h, a.k, a.c, a.spp),
+            "B": a.b, "spp": a.spp, "H": a.h, "W": a.w, "K": a.k, "C": a.c,
+            "l2_policy": "inputs larger than L2 (6.5 GB of weights per call, a "
+                         "different weight buffer per sample index)"}
+
+
+# --------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# --------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, power) if p >= 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(smax),
+                "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the CPU restatement on the host cores
+# --------------------------------------------------------------------------
+def cpu_sample(a, target_seconds, reps_min=1):
+    """Times oracle fwd+bwd on one image of the workload ([1,C,H,W] x
+    [1,K,K,H,W]); returns (Msamples/s, cores, description, seconds per rep)."""
+    import torch as th
+    import oracle
+    th.manual_seed(0)
+    data = 2 * th.randn(1, a.c, a.h, a.w)
+    weights = th.randn(1, a.k, a.k, a.h, a.w)
+    d_out = th.randn(1, a.c, a.h, a.w)
+    d_sw = th.randn(1, a.h, a.w)
+    out = th.empty_like(data); sum_w = th.empty(1, a.h, a.w)
+    d_data = th.empty_like(data); d_weights = th.empty_like(weights)
+
+    def once():
+        oracle.kernel_weighting_cpu_float32(data, weights, out, sum_w)
+        oracle.kernel_weighting_grad_cpu_float32(data, weights, sum_w, d_out, d_sw,
+                                                 d_data, d_weights)
+    once()                                   # warm-up (page faults, thread pool)
+    t0 = time.perf_counter(); once(); one = time.perf_counter() - t0
+    reps = max(reps_min, min(50, int(target_seconds / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    dt = (time.perf_counter() - t0) / reps
+    samples = a.h * a.w
+    desc = ("1 of the %d images of one call: [1,%d,%d,%d]x[1,%d,%d,%d,%d] fwd+bwd, "
+            "%d reps, OpenMP C restatement of the Halide CPU schedule (oracle/sbmc_oracle.c)"
+            % (a.b, a.c, a.h, a.w, a.k, a.k, a.h, a.w, reps))
+    return samples / dt / 1e6, oracle.num_threads(), desc, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_steps = []
+    import torch as th
+    import oracle
+    th.manual_seed(0)
+    data = 2 * th.randn(1, a.c, a.h, a.w)
+    weights = th.randn(1, a.k, a.k, a.h, a.w)
+    d_out = th.randn(1, a.c, a.h, a.w)
+    d_sw = th.randn(1, a.h, a.w)
+    out = th.empty_like(data); sum_w = th.empty(1, a.h, a.w)
+    d_data = th.empty_like(data); d_weights = th.empty_like(weights)
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        oracle.kernel_weighting_cpu_float32(data, weights, out, sum_w)
+        oracle.kernel_weighting_grad_cpu_float32(data, weights, sum_w, d_out, d_sw,
+                                                 d_data, d_weights)
+        if i >= a.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    dt = sum(t_steps) / len(t_steps)
+    value = a.h * a.w / dt / 1e6
+    sample = ("each step = 1 image of the workload ([1,%d,%d,%d]x[1,%d,%d,%d,%d], fwd+bwd) "
+              "instead of B*spp=%d" % (a.c, a.h, a.w, a.k, a.k, a.h, a.w, a.b * a.spp))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload(a),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "Halide (the reference's code generator) cannot be built here; this is "
+                "the schedule-faithful C/OpenMP restatement of its CPU path",
+    }))
+
+
+# --------------------------------------------------------------------------
+# the B200 arm
+# --------------------------------------------------------------------------
+def run_b200(a):
+    import torch as th
+    import torch.distributed as dist
+    from sbmc_b200 import _lib, halide_ops
+    from sbmc_b200 import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not th.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, C, H, W, K, spp = a.b, a.c, a.h, a.w, a.k, a.spp
+    gen = th.Generator(device=dev).manual_seed(1234 + rank)
+    plan = sharding.BandPlan(H * world, world, K, K) if world > 1 else None
+    # resident inputs: one weight buffer per sample index (spp x 6.5 GB at config 2)
+    data = [2 * th.randn(B, C, H, W, device=dev, generator=gen) for _ in range(spp)]
+    weights = []
+    for _ in range(spp):
+        wt = th.empty(B, K, K, H, W, device=dev)
+        for b in range(B):                       # bounded temporaries
+            wt[b].normal_(generator=gen)
+        weights.append(wt)
+    d_out = th.randn(B, C, H, W, device=dev, generator=gen)
+    d_sw = th.randn(B, H, W, device=dev, generator=gen)
+    out = th.empty(B, C, H, W, device=dev)
+    sum_w = th.empty(B, H, W, device=dev)
+    d_data = th.empty(B, C, H, W, device=dev)
+    d_weights = th.empty(B, K, K, H, W, device=dev)
+
+    def step():
+        for s in range(spp):
+            if plan is None:
+                halide_ops.kernel_weighting_cuda_float32(data[s], weights[s], out, sum_w)
+                halide_ops.kernel_weighting_grad_cuda_float32(
+                    data[s], weights[s], sum_w, d_out, d_sw, d_data, d_weights)
+            else:
+                ext = sharding.kernel_weighting_fwd_sharded(
+                    plan, rank, data[s], weights[s], out, sum_w)
+                sharding.kernel_weighting_bwd_sharded(
+                    plan, rank, data[s], weights[s], d_out, d_sw, d_data, d_weights,
+                    data_ext=ext)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.timing_collect()
+    _lib.timing_enable(True)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    _lib.timing_enable(False)
+    kernels = _lib.timing_collect()
+    clocks = sampler.stop() if rank == 0 else None
+    t = th.tensor([ms], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / a.steps
+    samples_step = B * spp * H * W * world
+    value = samples_step / (ms_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (largest share of the step)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks \
+        else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    per_sample = {"kw_fwd": 4 * (K * K + 2 * C + 1),            # W + D -> out + sum_w
+                  "kw_bwd_dweights": 4 * (K * K + 2 * C + 1),   # D + dO + dSw -> dW
+                  "kw_bwd_ddata": 4 * (K * K + 2 * C)}          # W + dO -> dD
+    launch_samples = B * H * W
+    table = {}
+    for name, (kms, cnt) in kernels.items():
+        if name in per_sample and cnt:
+            gbs = per_sample[name] * launch_samples / (kms / cnt * 1e-3) / 1e9
+            table[name] = {"launches": cnt, "avg_ms": kms / cnt, "GB/s": gbs,
+                           "frac": gbs / peak, "share_of_step": kms / (ms_step * a.steps)}
+    roofline = None
+    if table:
+        top = max(table, key=lambda n: table[n]["avg_ms"] * table[n]["launches"])
+        roofline = {"bound": "hbm", "kernel": top, "achieved": table[top]["GB/s"],
+                    "peak": peak, "unit": "GB/s", "frac": table[top]["frac"],
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_sample[top] * launch_samples,
+                    "step_frac": 4 * (2 * K * K + K * K + 5 * C + 2) * samples_step / world
+                    / (ms_step * 1e-3) / 1e9 / peak,
+                    "kernels": table}
+
+    # e2e: the same step through the host-buffer entry points (pinned host memory)
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, th, halide_ops, dev, world, dist)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cores, desc, _ = cpu_sample(a, a.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload(a),
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        if world > 1:
+            line["config"]["parallelism"] = (
+                "H-sharding: %d row bands of %d rows, NCCL halo exchange of %d data rows "
+                "(fwd) and d_data rows (bwd) per call" % (world, H, K - 1))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(a, th, halide_ops, dev, world, dist):
+    """One step = spp calls of fwd+bwd through the *_cpu_float32 entry points
+    (HOST tensors, pinned): every call streams its inputs H2D and its outputs
+    D2H inside the timed region."""
+    B, C, H, W, K, spp = a.b, a.c, a.h, a.w, a.k, a.spp
+    pin = dict(pin_memory=True)
+    data = th.randn(B, C, H, W, **pin).mul_(2)
+    weights = th.empty(B, K, K, H, W, **pin)
+    weights[0].normal_()
+    for b in range(1, B):                 # values do not matter for the timing
+        weights[b].copy_(weights[0])
+    d_out = th.randn(B, C, H, W, **pin)
+    d_sw = th.randn(B, H, W, **pin)
+    out = th.empty(B, C, H, W, **pin)
+    sum_w = th.empty(B, H, W, **pin)
+    d_data = th.empty(B, C, H, W, **pin)
+    d_weights = th.empty(B, K, K, H, W, **pin)
+
+    def step():
+        for _ in range(spp):
+            halide_ops.kernel_weighting_cpu_float32(data, weights, out, sum_w)
+            halide_ops.kernel_weighting_grad_cpu_float32(
+                data, weights, sum_w, d_out, d_sw, d_data, d_weights)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    # warm-up: one call pair (allocates the staging buffers)
+    halide_ops.kernel_weighting_cpu_float32(data, weights, out, sum_w)
+    halide_ops.kernel_weighting_grad_cpu_float32(data, weights, sum_w, d_out, d_sw,
+                                                 d_data, d_weights)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = th.tensor([dt], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = t.item() / a.e2e_steps
+    nb = lambda x: x.numel() * 4
+    h2d = spp * (2 * nb(weights) + 2 * nb(data) + nb(d_out) + nb(d_sw))
+    d2h = spp * (nb(out) + nb(sum_w) + nb(d_data) + nb(d_weights))
+    return {"value": B * spp * H * W * world / dt / 1e6, "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": a.e2e_steps, "ms_per_step": dt * 1e3,
+            "api": "sbmc_b200.halide_ops.kernel_weighting{,_grad}_cpu_float32 "
+                   "(sbmc_kernel_weighting_{fwd,bwd}_host_f32), pinned host tensors"}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/*
+ * sbmc_b200.h -- C ABI of the B200-native SBMC kernel-splatting library
+ * (libsbmc_b200.so, built from sbmc_b200/csrc/ with nvcc for sm_100a).
+ *
+ * These entry points are what a binding for the reference's native-op module
+ * `sbmc.halide_ops` would call.  The reference binds six functions
+ * (reference setup.py:65-84, pybind `m.def` synthesised at
+ * halide_pytorch/halide_pytorch/extension.py:168-173) whose arguments are the
+ * Halide Input<>s then Output<>s in declaration order:
+ *
+ *   scatter2gather_{cpu,cuda}_float32(weights, output)
+ *       src/scatter2gather.cpp:61-62, called at sbmc/functions.py:56-59,67-70
+ *   kernel_weighting_{cpu,cuda}_float32(data, weights, output, sum_w)
+ *       src/kernel_weighting.cpp:130-133, called at sbmc/functions.py:95-98
+ *   kernel_weighting_grad_{cpu,cuda}_float32(data, weights, sum_w, d_output,
+ *                                            d_sum_w, d_data, d_weights)
+ *       src/kernel_weighting.cpp:195-202, called at sbmc/functions.py:109-114
+ *
+ * Conventions (all functions):
+ *   - plain C, no torch / Halide types; fp32, contiguous, torch index order:
+ *       data[n][c][y][x]   weights[n][dy][dx][y][x]   sum_w[n][y][x]
+ *   - the caller owns and allocates every buffer; outputs are fully
+ *     overwritten (they may be uninitialised on entry, as in
+ *     sbmc/functions.py:53-54,91-94,105-108); nothing is retained.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); device
+ *     entry points are asynchronous with respect to the host.
+ *   - return 0 on success, a negative SBMC_E* code otherwise; never throws.
+ *     sbmc_b200_last_error() gives a thread-local message for the last failure.
+ *   - kernel sizes: any kh, kw >= 1 (centre (k-1)/2, floor, as in
+ *     src/kernel_weighting.cpp:53-54), any c >= 1, 64-bit element counts.
+ *   - zero is read outside the image for data, weights and d_output
+ *     (BoundaryConditions::constant_exterior, src/kernel_weighting.cpp:35-39,
+ *     78-85; src/scatter2gather.cpp:34-35).
+ */
+#ifndef SBMC_B200_H_
+#define SBMC_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SBMC_API __attribute__((visibility("default")))
+#else
+#define SBMC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBMC_OK 0
+#define SBMC_EINVAL (-1)   /* bad argument (null pointer, negative size, ...) */
+#define SBMC_ECUDA (-2)    /* a CUDA runtime / driver call failed             */
+#define SBMC_ENODEV (-3)   /* no sm_100 device / driver available             */
+#define SBMC_EALIGN (-4)   /* pointer not 4-byte aligned                      */
+
+/* Library version (major*10000 + minor*100 + patch). */
+SBMC_API int sbmc_b200_version(void);
+
+/* Message for the last error on the calling thread ("" if none). */
+SBMC_API const char *sbmc_b200_last_error(void);
+
+/* 0: pick the tuned sm_100a kernels when the shape allows (default);
+ * 1: always run the shape-generic kernels (used by the parity tests to check
+ *    both implementations against the oracle).  Returns the previous value. */
+SBMC_API int sbmc_b200_force_generic(int flag);
+
+/* Which implementation the last call on this thread used:
+ * 0 = none yet, 1 = tuned (TMA / vectorised) kernels, 2 = generic kernels. */
+SBMC_API int sbmc_b200_last_path(void);
+
+/* Number of kernels this library has launched since load (all threads). */
+SBMC_API int64_t sbmc_b200_launch_count(void);
+
+/* Per-kernel device timing for benchmarks.  While enabled, each kernel the
+ * library launches is bracketed by CUDA events on its stream.
+ * sbmc_b200_timing_collect waits for them and writes, per kernel kind, the
+ * summed device time in ms and the number of launches since the last collect
+ * (arrays of SBMC_NUM_KERNEL_KINDS entries; either may be NULL). */
+#define SBMC_KERNEL_KW_FWD 0       /* KernelWeighting forward                */
+#define SBMC_KERNEL_KW_DWEIGHTS 1  /* backward, d_weights (write stream)     */
+#define SBMC_KERNEL_KW_DDATA 2     /* backward, d_data (reads the weights)   */
+#define SBMC_KERNEL_S2G 3          /* Scatter2Gather                         */
+#define SBMC_KERNEL_OTHER 4        /* memsets / halo adds / fused splat ...  */
+#define SBMC_NUM_KERNEL_KINDS 8
+SBMC_API int sbmc_b200_timing_enable(int flag);
+SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
+
+/* ---- device-pointer entry points (replace the *_cuda_float32 ops) -------- */
+
+/* gather[n][dy][dx][y][x] = scatter[n][kh-1-dy][kw-1-dx][y+dy-c0h][x+dx-c0w]
+ * (0 if the source pixel is outside the image).  Bit-exact copy.
+ * Replaces scatter2gather_cuda_float32 (src/scatter2gather.cpp:28-52). */
+SBMC_API int sbmc_scatter2gather_f32(const float *scatter, float *gather, int64_t n,
+                            int kh, int kw, int64_t h, int64_t w, void *stream);
+
+/* output[n][c][y][x] = sum_{dy,dx} weights[n][dy][dx][y][x]
+ *                                  * data[n][c][y+dy-c0h][x+dx-c0w]
+ * sum_w[n][y][x]     = sum_{dy,dx} weights[n][dy][dx][y][x]   (all taps)
+ * Replaces kernel_weighting_cuda_float32 (src/kernel_weighting.cpp:27-64). */
+SBMC_API int sbmc_kernel_weighting_fwd_f32(const float *data, const float *weights,
+                                  float *output, float *sum_w, int64_t n, int c,
+                                  int64_t h, int64_t w, int kh, int kw,
+                                  void *stream);
+
+/* d_data[n][c][y][x]      = sum_{ry,rx} weights[n][kh-1-ry][kw-1-rx][y+ry-c0h][x+rx-c0w]
+ *                                       * d_output[n][c][y+ry-c0h][x+rx-c0w]
+ * d_weights[n][dy][dx][y][x] = d_sum_w[n][y][x]
+ *                              + sum_c data[n][c][y+dy-c0h][x+dx-c0w] * d_output[n][c][y][x]
+ * `sum_w` is accepted for signature parity and never read (it is unused by the
+ * reference pipeline too, src/kernel_weighting.cpp:67-124); it may be NULL.
+ * Replaces kernel_weighting_grad_cuda_float32. */
+SBMC_API int sbmc_kernel_weighting_bwd_f32(const float *data, const float *weights,
+                                  const float *sum_w, const float *d_output,
+                                  const float *d_sum_w, float *d_data,
+                                  float *d_weights, int64_t n, int c, int64_t h,
+                                  int64_t w, int kh, int kw, void *stream);
+
+/* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
+ * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /
+ * d_sum_w / d_weights cover exactly the band.  `data_ext` ([n][c][halo_top +
+ * h + halo_bot][w]) carries the band plus real neighbour rows above / below
+ * (from the adjacent band, or zeros at the image border); rows outside
+ * data_ext read as zero.  `d_data_ext` has the same extended shape: the band's
+ * samples scatter gradient into their neighbours' rows, which the caller adds
+ * to the adjacent bands.  halo_* = 0 gives the plain ops.
+ */
+SBMC_API int sbmc_kernel_weighting_fwd_band_f32(const float *data_ext,
+                                       const float *weights, float *output,
+                                       float *sum_w, int64_t n, int c, int64_t h,
+                                       int64_t w, int kh, int kw, int halo_top,
+                                       int halo_bot, void *stream);
+
+SBMC_API int sbmc_kernel_weighting_bwd_band_f32(const float *data_ext,
+                                       const float *weights,
+                                       const float *d_output,
+                                       const float *d_sum_w, float *d_data_ext,
+                                       float *d_weights, int64_t n, int c,
+                                       int64_t h, int64_t w, int kh, int kw,
+                                       int halo_top, int halo_bot, void *stream);
+
+/* ---- host-pointer entry points (replace the *_cpu_float32 ops) ----------- *
+ * Same semantics with HOST buffers (pageable or pinned): the library streams
+ * row bands through the GPU `device` (H2D, kernel, D2H overlapped on several
+ * streams) and returns when the host outputs are complete.  There is no CPU
+ * compute path in this library.
+ */
+SBMC_API int sbmc_scatter2gather_host_f32(const float *scatter, float *gather, int64_t n,
+                                 int kh, int kw, int64_t h, int64_t w,
+                                 int device);
+
+SBMC_API int sbmc_kernel_weighting_fwd_host_f32(const float *data, const float *weights,
+                                       float *output, float *sum_w, int64_t n,
+                                       int c, int64_t h, int64_t w, int kh,
+                                       int kw, int device);
+
+SBMC_API int sbmc_kernel_weighting_bwd_host_f32(const float *data, const float *weights,
+                                       const float *sum_w, const float *d_output,
+                                       const float *d_sum_w, float *d_data,
+                                       float *d_weights, int64_t n, int c,
+                                       int64_t h, int64_t w, int kh, int kw,
+                                       int device);
+
+/* Release the cached device staging buffers of the host entry points. */
+SBMC_API int sbmc_b200_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBMC_B200_H_ */

@@ -1,0 +1,111 @@
+"""ctypes binding of libsbmc_b200.so (C ABI declared in include/sbmc_b200.h).
+
+PyTorch is only used by the callers for device memory and streams; the library
+itself takes raw pointers.  There is no CPU or PyTorch fallback: if the library
+is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbmc_b200.so")
+
+_i64, _int, _ptr = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/sbmc_b200.h one to one.
+SIGNATURES = {
+    "sbmc_b200_version": (_int, []),
+    "sbmc_b200_last_error": (ctypes.c_char_p, []),
+    "sbmc_b200_force_generic": (_int, [_int]),
+    "sbmc_b200_last_path": (_int, []),
+    "sbmc_b200_launch_count": (_i64, []),
+    "sbmc_b200_timing_enable": (_int, [_int]),
+    "sbmc_b200_timing_collect": (_int, [_ptr, _ptr]),
+    "sbmc_scatter2gather_f32":
+        (_int, [_ptr, _ptr, _i64, _int, _int, _i64, _i64, _ptr]),
+    "sbmc_kernel_weighting_fwd_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _ptr]),
+    "sbmc_kernel_weighting_bwd_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64,
+                _int, _int, _ptr]),
+    "sbmc_kernel_weighting_fwd_band_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
+                _int, _ptr]),
+    "sbmc_kernel_weighting_bwd_band_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int,
+                _int, _int, _int, _ptr]),
+    "sbmc_scatter2gather_host_f32":
+        (_int, [_ptr, _ptr, _i64, _int, _int, _i64, _i64, _int]),
+    "sbmc_kernel_weighting_fwd_host_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int]),
+    "sbmc_kernel_weighting_bwd_host_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64,
+                _int, _int, _int]),
+    "sbmc_b200_host_release": (_int, []),
+}
+
+_lib = None
+
+
+class SbmcB200Error(RuntimeError):
+    """A libsbmc_b200 call returned a non-zero status."""
+
+
+def load():
+    """Load the shared library (building it with nvcc first if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise SbmcB200Error(
+            "libsbmc_b200.so could not be loaded (%s); there is no fallback "
+            "path -- build it with `python -m sbmc_b200.build`" % e)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().sbmc_b200_last_error()
+        raise SbmcB200Error("%s failed (code %d): %s" % (
+            what, rc, msg.decode("utf-8", "replace") if msg else ""))
+
+
+def launch_count():
+    return int(load().sbmc_b200_launch_count())
+
+
+def force_generic(flag):
+    return int(load().sbmc_b200_force_generic(1 if flag else 0))
+
+
+def last_path():
+    return int(load().sbmc_b200_last_path())
+
+
+KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
+                4: "other"}
+NUM_KERNEL_KINDS = 8
+
+
+def timing_enable(flag):
+    return int(load().sbmc_b200_timing_enable(1 if flag else 0))
+
+
+def timing_collect():
+    """{kernel kind: (device ms, launches)} since the previous collect."""
+    ms = (ctypes.c_double * NUM_KERNEL_KINDS)()
+    cnt = (ctypes.c_int64 * NUM_KERNEL_KINDS)()
+    check(load().sbmc_b200_timing_collect(ctypes.cast(ms, _ptr), ctypes.cast(cnt, _ptr)),
+          "timing_collect")
+    return {KERNEL_KINDS.get(k, "kind%d" % k): (ms[k], int(cnt[k]))
+            for k in range(NUM_KERNEL_KINDS) if cnt[k]}

@@ -1,0 +1,81 @@
+"""Builds libsbmc_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+No torch involvement: the library is plain CUDA behind ``extern "C"`` entry
+points (include/sbmc_b200.h).  nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+LIB_PATH = os.path.join(HERE, "libsbmc_b200.so")
+SOURCES = ["runtime.cu", "generic.cu", "kw_launch.cu", "s2g.cu", "capi.cu",
+           "host_stream.cu", "splat.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+    "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xptxas=-v",
+]
+
+
+def _nvcc():
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; cannot build libsbmc_b200.so")
+    return cand
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES
+            if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into one shared library; returns its path."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in _sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(
+            cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    logs = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        logs.append("== %s\n%s" % (os.path.basename(src), out))
+        failed |= p.returncode != 0
+    log = "\n".join(logs)
+    with open(os.path.join(HERE, "build", "nvcc.log"), "w") as fid:
+        fid.write(log)
+    if failed:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libsbmc_b200.so")
+    if verbose:
+        print(log)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + [
+        "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+        "-Xlinker", "--exclude-libs,ALL"]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,218 @@
+"""H-sharding of the kernel-weighting path across GPUs (one process per GPU).
+
+The reference is single-device; its only mechanism for
+large images is overlap-tiling with recompute (scripts/denoise.py:54-93).  Every
+output pixel of KernelWeighting depends on a K x K neighbourhood only, so the
+image is cut into contiguous row bands, one per rank, and instead of recomputing
+the overlap the ranks exchange it:
+
+* forward / d_weights read `data` rows up to c0 = (K-1)//2 above and K-1-c0
+  below the band  ->  each rank receives those rows from its two neighbours
+  (`exchange_halo`, one grouped NCCL send/recv per call, [B, C, <=K-1, W] floats);
+* d_data is a scatter: a band's samples contribute to rows up to K-1-c0 above
+  and c0 below the band  ->  each rank computes its partial d_data on band+halo
+  rows and the halo rows are sent to the neighbours, which add them
+  (`reduce_halo`).  The K*K-channel weight tensor never crosses the link.
+
+The exchange is written against torch.distributed point-to-point ops only, so it
+runs over NCCL/NVLink on GPUs and over gloo on CPU tensors (tests/test_sharding.py
+drives it with world_size 2 on CPU).  The compute goes through the row-band
+entry points of the C ABI (sbmc_kernel_weighting_{fwd,bwd}_band_f32).
+"""
+import torch as th
+import torch.distributed as dist
+
+from . import _lib
+
+__all__ = ["BandPlan", "exchange_halo", "reduce_halo", "kernel_weighting_fwd_sharded",
+           "kernel_weighting_bwd_sharded", "ShardedKernelWeighting", "gather_bands"]
+
+
+class BandPlan:
+    """Contiguous row bands of an image of `height` rows over `world` ranks.
+
+    Rows are split as evenly as possible (the first `height % world` bands get
+    one extra row).  `pad` = K-1-c0 >= c0 is the halo kept on both sides of a
+    band (clamped at the image border), which covers the rows read by
+    forward / d_weights and the rows reached by d_data for odd and even K.
+    """
+
+    def __init__(self, height, world, kh, kw=None):
+        if height < world:
+            raise ValueError("cannot split %d rows over %d ranks" % (height, world))
+        self.height, self.world, self.kh, self.kw = height, world, kh, kw or kh
+        c0 = (kh - 1) // 2
+        self.pad = max(c0, kh - 1 - c0)
+        base, extra = divmod(height, world)
+        self.y0, self.y1 = [], []
+        y = 0
+        for r in range(world):
+            rows = base + (1 if r < extra else 0)
+            self.y0.append(y)
+            y += rows
+            self.y1.append(y)
+        if world > 1 and min(b - a for a, b in zip(self.y0, self.y1)) < self.pad:
+            raise ValueError("bands (%d rows) are shorter than the halo (%d rows)"
+                             % (base, self.pad))
+
+    def rows(self, rank):
+        return self.y1[rank] - self.y0[rank]
+
+    def halo_top(self, rank):
+        return min(self.pad, self.y0[rank])
+
+    def halo_bot(self, rank):
+        return min(self.pad, self.height - self.y1[rank])
+
+    def band(self, rank, full, dim):
+        """The slice of a full-image tensor that `rank` owns along `dim`."""
+        return full.narrow(dim, self.y0[rank], self.rows(rank))
+
+
+def _p2p(ops, group):
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def exchange_halo(plan, rank, band, group=None):
+    """band [..., rows, W] -> ext [..., top + rows + bot, W] with the neighbours'
+    rows in the halos (image borders have no halo).  One grouped send/recv."""
+    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    rows = band.shape[-2]
+    ext = band.new_empty(band.shape[:-2] + (top + rows + bot, band.shape[-1]))
+    ext.narrow(-2, top, rows).copy_(band)
+    ops, recv = [], []
+    if top:      # neighbour above: it needs my first rows, I need its last rows
+        up = rank - 1
+        send = band.narrow(-2, 0, plan.halo_bot(up)).contiguous()
+        buf = band.new_empty(band.shape[:-2] + (top, band.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, buf, up, group)]
+        recv.append((0, top, buf))
+    if bot:
+        dn = rank + 1
+        send = band.narrow(-2, rows - plan.halo_top(dn), plan.halo_top(dn)).contiguous()
+        buf = band.new_empty(band.shape[:-2] + (bot, band.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, dn, group), dist.P2POp(dist.irecv, buf, dn, group)]
+        recv.append((top + rows, bot, buf))
+    _p2p(ops, group)
+    for start, count, buf in recv:
+        ext.narrow(-2, start, count).copy_(buf)
+    return ext
+
+
+def reduce_halo(plan, rank, ext, out=None, group=None):
+    """Adjoint of exchange_halo: ext [..., top + rows + bot, W] holds this rank's
+    partial sums for its band and for the neighbours' edge rows; the halo rows
+    are sent to the neighbours and theirs are added to the band.  Returns the
+    band [..., rows, W] (written into `out` if given)."""
+    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    rows = ext.shape[-2] - top - bot
+    band = ext.narrow(-2, top, rows)
+    if out is None:
+        out = band.clone()
+    else:
+        out.copy_(band)
+    ops, recv = [], []
+    if top:
+        up = rank - 1
+        send = ext.narrow(-2, 0, top).contiguous()
+        cnt = plan.halo_bot(up)          # rows of mine the upper band reached
+        buf = ext.new_empty(ext.shape[:-2] + (cnt, ext.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, buf, up, group)]
+        recv.append((0, cnt, buf))
+    if bot:
+        dn = rank + 1
+        send = ext.narrow(-2, top + rows, bot).contiguous()
+        cnt = plan.halo_top(dn)
+        buf = ext.new_empty(ext.shape[:-2] + (cnt, ext.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, dn, group), dist.P2POp(dist.irecv, buf, dn, group)]
+        recv.append((rows - cnt, cnt, buf))
+    _p2p(ops, group)
+    for start, count, buf in recv:
+        out.narrow(-2, start, count).add_(buf)
+    return out
+
+
+def _stream(t):
+    return th.cuda.current_stream(t.device).cuda_stream
+
+
+def kernel_weighting_fwd_sharded(plan, rank, data, weights, output, sum_w, group=None,
+                                 data_ext=None):
+    """KernelWeighting forward on this rank's band.  data [B,C,rows,W] and weights
+    [B,K,K,rows,W] are the band's slices; output / sum_w are caller-allocated
+    (reference ownership rule, sbmc/functions.py:91-94).  Returns data_ext so the
+    backward pass can reuse it."""
+    if data_ext is None:
+        data_ext = exchange_halo(plan, rank, data, group)
+    n, c, rows, w = data.shape
+    _, kh, kw, _, _ = weights.shape
+    lib = _lib.load()
+    with th.cuda.device(data.device):
+        _lib.check(lib.sbmc_kernel_weighting_fwd_band_f32(
+            data_ext.data_ptr(), weights.data_ptr(), output.data_ptr(), sum_w.data_ptr(),
+            n, c, rows, w, kh, kw, plan.halo_top(rank), plan.halo_bot(rank),
+            _stream(data)), "kernel_weighting (band)")
+    return data_ext
+
+
+def kernel_weighting_bwd_sharded(plan, rank, data, weights, d_output, d_sum_w, d_data,
+                                 d_weights, group=None, data_ext=None):
+    """KernelWeighting backward on this rank's band (see module docstring)."""
+    if data_ext is None:
+        data_ext = exchange_halo(plan, rank, data, group)
+    n, c, rows, w = data.shape
+    _, kh, kw, _, _ = weights.shape
+    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    d_data_ext = th.empty_like(data_ext)
+    lib = _lib.load()
+    with th.cuda.device(data.device):
+        _lib.check(lib.sbmc_kernel_weighting_bwd_band_f32(
+            data_ext.data_ptr(), weights.data_ptr(), d_output.data_ptr(),
+            d_sum_w.data_ptr(), d_data_ext.data_ptr(), d_weights.data_ptr(),
+            n, c, rows, w, kh, kw, top, bot, _stream(data)), "kernel_weighting_grad (band)")
+    reduce_halo(plan, rank, d_data_ext, out=d_data, group=group)
+    return d_data
+
+
+class ShardedKernelWeighting(th.autograd.Function):
+    """`KernelWeighting` (sbmc/functions.py:74-115) on one row band per rank:
+    same (output, sum_w) / (d_data, d_weights) contract for the band's slices."""
+
+    @staticmethod
+    def forward(ctx, data, weights, plan, rank, group=None):
+        data = data.contiguous()
+        weights = weights.contiguous()
+        n, c, rows, w = data.shape
+        output = th.empty_like(data)
+        sum_w = data.new_empty((n, rows, w))
+        data_ext = kernel_weighting_fwd_sharded(plan, rank, data, weights, output, sum_w, group)
+        ctx.save_for_backward(data, weights, data_ext)
+        ctx.plan, ctx.rank, ctx.group = plan, rank, group
+        return output, sum_w
+
+    @staticmethod
+    def backward(ctx, d_output, d_sum_w):
+        data, weights, data_ext = ctx.saved_tensors
+        d_data = th.empty_like(data)
+        d_weights = th.empty_like(weights)
+        kernel_weighting_bwd_sharded(ctx.plan, ctx.rank, data, weights,
+                                     d_output.contiguous(), d_sum_w.contiguous(), d_data,
+                                     d_weights, ctx.group, data_ext)
+        return d_data, d_weights, None, None, None
+
+
+def gather_bands(plan, rank, band, dim, group=None):
+    """Final gather: every rank ends with the full tensor (bands concatenated
+    along `dim`).  Bands may differ by one row, so this is an all_gather of
+    padded slices followed by a trim."""
+    world = plan.world
+    rows_max = max(plan.rows(r) for r in range(world))
+    moved = band.movedim(dim, 0).contiguous()
+    padded = moved.new_zeros((rows_max,) + moved.shape[1:])
+    padded[:moved.shape[0]].copy_(moved)
+    parts = [th.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    full = th.cat([p[:plan.rows(r)] for r, p in enumerate(parts)], dim=0)
+    return full.movedim(0, dim).contiguous()

@@ -1,0 +1,28 @@
+"""pytest configuration: the ``gpu`` marker and shared helpers.
+
+``-m "not gpu"`` runs on a CPU-only box (oracle vs golden vectors, host logic,
+C-ABI symbol table, gloo world_size-2 sharding); ``-m gpu`` runs the parity
+tests proper through the C ABI on a B200.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -1,0 +1,102 @@
+"""CPU suite: the C-ABI library loads without a GPU and exports every symbol
+that include/sbmc_b200.h declares; argument validation happens before any CUDA
+call; the Python drop-in module fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch as th
+
+from sbmc_b200 import _lib, halide_ops
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                      "include", "sbmc_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"SBMC_API\s+[\w\s\*]+?\b(sbmc_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for want in ("sbmc_scatter2gather_f32", "sbmc_kernel_weighting_fwd_f32",
+                 "sbmc_kernel_weighting_bwd_f32", "sbmc_scatter2gather_host_f32",
+                 "sbmc_kernel_weighting_fwd_host_f32",
+                 "sbmc_kernel_weighting_bwd_host_f32"):
+        assert want in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.load()
+    for name in declared_symbols():
+        assert hasattr(lib, name), "missing export: " + name
+
+
+def test_python_binding_covers_every_declared_symbol():
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.sbmc_b200_version() >= 100
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _lib.load()
+    # negative sizes / zero kernel -> SBMC_EINVAL, with a message
+    rc = lib.sbmc_kernel_weighting_fwd_f32(None, None, None, None, -1, 3, 4, 4, 3, 3, None)
+    assert rc == -1
+    assert b"invalid shape" in lib.sbmc_b200_last_error()
+    rc = lib.sbmc_scatter2gather_f32(None, None, 1, 0, 3, 4, 4, None)
+    assert rc == -1
+    # empty problems succeed without touching the device
+    assert lib.sbmc_kernel_weighting_fwd_f32(None, None, None, None, 0, 3, 4, 4, 3, 3, None) == 0
+    assert lib.sbmc_scatter2gather_f32(None, None, 2, 3, 3, 0, 4, None) == 0
+    # null pointers on a non-empty problem
+    rc = lib.sbmc_kernel_weighting_fwd_f32(None, None, None, None, 1, 3, 4, 4, 3, 3, None)
+    assert rc == -1
+    with pytest.raises(_lib.SbmcB200Error):
+        _lib.check(rc, "kernel_weighting")
+
+
+def test_drop_in_module_has_the_reference_names():
+    # reference setup.py:65-84
+    for op in ("scatter2gather", "kernel_weighting", "kernel_weighting_grad"):
+        for dev in ("cpu", "cuda"):
+            assert callable(getattr(halide_ops, "%s_%s_float32" % (op, dev)))
+
+
+def test_drop_in_module_rejects_bad_tensors():
+    w = th.zeros(1, 3, 3, 4, 4)
+    with pytest.raises(RuntimeError, match="float32"):
+        halide_ops.scatter2gather_cpu_float32(w.double(), w.double())
+    with pytest.raises(RuntimeError, match="contiguous"):
+        halide_ops.scatter2gather_cpu_float32(w.transpose(3, 4), w)
+    with pytest.raises(RuntimeError, match="dimensions"):
+        halide_ops.scatter2gather_cpu_float32(w[0], w[0])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        halide_ops.scatter2gather_cuda_float32(w, w.clone())
+    d = th.zeros(1, 3, 4, 4)
+    with pytest.raises(RuntimeError, match="shape"):
+        halide_ops.kernel_weighting_cpu_float32(d, w, d.clone(), th.zeros(1, 4, 5))
+
+
+@pytest.mark.skipif(th.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    """Host tensors are streamed through a GPU; without one the op must raise."""
+    import sbmc_b200.functions as funcs
+    w = th.zeros(1, 3, 3, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU compute path"):
+        funcs.Scatter2Gather.apply(w)
+    with pytest.raises(RuntimeError, match="no CPU compute path"):
+        funcs.KernelWeighting.apply(th.zeros(1, 3, 4, 4), w)
+
+
+def test_product_does_not_import_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "sbmc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "sbmc_oracle" not in text, f

@@ -1,0 +1,119 @@
+// sweep.cu -- tuning sweep for the KernelWeighting kernels (developer tool, not
+// part of the library).  Times every compiled (ROWS/NSEG, MINB, CH) variant of
+// the forward, d_weights and d_data kernels on the BASELINE config-2 call shape
+// (N=4, C=3, 720x1280, K=21) with CUDA events and prints achieved GB/s against
+// the algorithmic bytes.  Build: see tools/build_sweep.sh.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../sbmc_b200/csrc/kw_launch.cuh"
+
+using namespace sbmc;
+
+#define CK(x)                                                                 \
+  do {                                                                        \
+    cudaError_t e = (x);                                                      \
+    if (e != cudaSuccess) {                                                   \
+      fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e));                 \
+      exit(1);                                                                \
+    }                                                                         \
+  } while (0)
+
+__global__ void fill_kernel(float *p, size_t n, unsigned seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)(i * 2654435761u) ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = (float)(h & 0xffff) / 65536.0f - 0.5f;
+  }
+}
+
+struct Ctx {
+  i64 n = 4, h = 720, w = 1280;
+  int k = 21;
+  float *data, *wt, *out, *sw, *dout, *dsw, *ddata, *dwt;
+  cudaStream_t st;
+  int iters = 5;
+};
+
+template <typename F>
+static void time_it(Ctx &c, const char *name, double bytes_per_sample, F &&f) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  for (int i = 0; i < 2; ++i) {
+    int rc = f();
+    if (rc) {
+      printf("%-44s FAILED rc=%d (%s)\n", name, rc, sbmc_b200_last_error());
+      return;
+    }
+  }
+  CK(cudaStreamSynchronize(c.st));
+  CK(cudaEventRecord(a, c.st));
+  for (int i = 0; i < c.iters; ++i) f();
+  CK(cudaEventRecord(b, c.st));
+  CK(cudaEventSynchronize(b));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  ms /= c.iters;
+  const double samples = (double)c.n * c.h * c.w;
+  printf("%-44s %8.3f ms  %8.1f GB/s  %8.1f Msamples/s\n", name, ms,
+         bytes_per_sample * samples / (ms * 1e-3) / 1e9, samples / (ms * 1e-3) / 1e6);
+  fflush(stdout);
+}
+
+#define FWD(ROWS, MINB, CH)                                                   \
+  time_it(c, "fwd  rows=" #ROWS " minb=" #MINB " ch=" #CH, 4.0 * (441 + 7), [&] { \
+    return run_fwd<3, 21, ROWS, MINB, CH>(c.data, c.wt, c.out, c.sw, c.n, c.h, c.w, \
+                                          c.k, 0, 0, c.st);                  \
+  });
+#define DWT(ROWS, MINB, CH)                                                   \
+  time_it(c, "dwt  rows=" #ROWS " minb=" #MINB " ch=" #CH, 4.0 * (441 + 7), [&] { \
+    return run_bwd_dweights<3, 21, ROWS, MINB, CH>(c.data, c.dout, c.dsw, c.dwt, c.n, \
+                                                   c.h, c.w, c.k, 0, 0, c.st); \
+  });
+#define DDA(NSEG, MINB, CH)                                                   \
+  time_it(c, "dda  nseg=" #NSEG " minb=" #MINB " ch=" #CH, 4.0 * (441 + 6), [&] { \
+    return run_bwd_ddata<3, 21, NSEG, MINB, CH>(c.wt, c.dout, c.ddata, c.n, c.h, c.w, \
+                                                c.k, 0, 0, c.st);             \
+  });
+
+int main(int argc, char **argv) {
+  Ctx c;
+  const char *which = argc > 1 ? argv[1] : "all";
+  if (argc > 2) c.n = atoi(argv[2]);
+  CK(cudaStreamCreate(&c.st));
+  const size_t img = (size_t)c.n * 3 * c.h * c.w, pl = (size_t)c.n * c.h * c.w;
+  const size_t vol = (size_t)c.n * c.k * c.k * c.h * c.w;
+  CK(cudaMalloc(&c.data, img * 4));  CK(cudaMalloc(&c.out, img * 4));
+  CK(cudaMalloc(&c.dout, img * 4));  CK(cudaMalloc(&c.ddata, img * 4));
+  CK(cudaMalloc(&c.sw, pl * 4));     CK(cudaMalloc(&c.dsw, pl * 4));
+  CK(cudaMalloc(&c.wt, vol * 4));    CK(cudaMalloc(&c.dwt, vol * 4));
+  fill_kernel<<<1184, 256>>>(c.data, img, 1);
+  fill_kernel<<<1184, 256>>>(c.dout, img, 2);
+  fill_kernel<<<1184, 256>>>(c.dsw, pl, 3);
+  fill_kernel<<<1184, 256>>>(c.wt, vol, 4);
+  CK(cudaDeviceSynchronize());
+  // reference points: device-to-device copy and memset of the weight volume
+  time_it(c, "memcpy d2d (R+W of the volume)", 4.0 * 441 * 2, [&] {
+    return (int)cudaMemcpyAsync(c.dwt, c.wt, vol * 4, cudaMemcpyDeviceToDevice, c.st);
+  });
+  time_it(c, "memset (W of the volume)", 4.0 * 441, [&] {
+    return (int)cudaMemsetAsync(c.dwt, 0, vol * 4, c.st);
+  });
+  const bool all = !strcmp(which, "all");
+  if (all || !strcmp(which, "fwd")) {
+    FWD(8, 2, 7) FWD(8, 2, 11) FWD(8, 2, 21) FWD(8, 3, 3) FWD(8, 3, 7) FWD(8, 1, 21)
+    FWD(4, 4, 7) FWD(4, 6, 3) FWD(16, 1, 7) FWD(16, 1, 11) FWD(4, 2, 21)
+  }
+  if (all || !strcmp(which, "dwt")) {
+    DWT(8, 2, 7) DWT(8, 3, 7) DWT(8, 4, 3) DWT(4, 4, 7) DWT(16, 1, 7) DWT(8, 2, 21)
+  }
+  if (all || !strcmp(which, "dda")) {
+    DDA(10, 1, 7) DDA(10, 1, 11) DDA(10, 1, 21) DDA(5, 2, 7) DDA(5, 1, 21) DDA(5, 1, 11)
+    DDA(2, 4, 7) DDA(2, 2, 21)
+  }
+  return 0;
+}

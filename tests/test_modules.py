@@ -1,0 +1,276 @@
+"""Module / model tests.  CPU suite: structure, error behaviour and state-dict
+names (reference tests/test_modules.py:18-60 and SURVEY.md appendix A), and the
+module logic with the two custom ops stood in for by the oracle.  GPU suite:
+the same known-answer tests and a float64 torch restatement, on the real ops."""
+import math
+
+import pytest
+import torch as th
+import torch.nn.functional as F
+
+from sbmc_b200 import functions as funcs
+from sbmc_b200 import models, modules
+from tests import kats
+
+
+@pytest.fixture
+def oracle_ops(monkeypatch):
+    """Run the module logic on CPU: the custom ops are replaced by the oracle
+    (test infrastructure; the product has no CPU path)."""
+    KW, S2G = kats.oracle_functions()
+    monkeypatch.setattr(funcs, "KernelWeighting", KW)
+    monkeypatch.setattr(funcs, "Scatter2Gather", S2G)
+
+
+def test_convchain_basic():
+    """reference tests/test_modules.py:18-60."""
+    with pytest.raises(ValueError):
+        modules.ConvChain(3, 3, depth=0)
+    with pytest.raises(ValueError):
+        modules.ConvChain(3, 3, depth=-1)
+    with pytest.raises(ValueError):
+        modules.ConvChain(3, 3, output_type="randomstring")
+    with pytest.raises(ValueError):
+        modules.ConvChain(3, 3, activation="randomstring")
+    with pytest.raises(ValueError):
+        modules.ConvChain(3, 3, normalize=True, normalization_type="randomstring")
+    for nrm in [False, True]:
+        net = modules.ConvChain(3, 3, depth=3, width=32, normalize=nrm)
+        idx = 1 if nrm else 0
+        assert isinstance(net.layer_0, modules.ConvChain._ConvBNRelu)
+        assert isinstance(net.layer_1, modules.ConvChain._ConvBNRelu)
+        assert isinstance(net.prediction, th.nn.Conv2d)
+        for layer, cin in ((net.layer_0, 3), (net.layer_1, 32)):
+            l = list(layer.layer.children())
+            assert isinstance(l[0], th.nn.Conv2d) and isinstance(l[1 + idx], th.nn.ReLU)
+            assert l[0].kernel_size == (3, 3) and l[0].stride == (1, 1)
+            assert l[0].in_channels == cin and l[0].out_channels == 32
+            if nrm:
+                assert isinstance(l[1], th.nn.BatchNorm2d)
+        assert net.prediction.in_channels == 32 and net.prediction.out_channels == 3
+        assert net.prediction.kernel_size == (3, 3)
+        y = net(th.randn(1, 3, 8, 8))
+        assert y.shape == (1, 3, 8, 8)
+    assert modules.ConvChain(3, 5, ksize=5, pad=False, depth=2)(th.randn(1, 3, 12, 12)).shape \
+        == (1, 5, 4, 4)
+
+
+def test_multisteps_structure_and_state_dict_names():
+    """layer shapes and parameter names of Multisteps(93, 3)."""
+    with pytest.raises(ValueError):
+        models.Multisteps(93, 3, ksize=4)
+    with pytest.raises(ValueError):
+        models.Multisteps(93, 3, ksize=1)
+    with pytest.raises(ValueError):
+        models.Multisteps(93, 3, nsteps=0)
+    net = models.Multisteps(93, 3)
+    sd = net.state_dict()
+    shapes = {
+        "embedding_00.layer_0.layer.0.weight_v": (128, 96, 1, 1),
+        "embedding_00.layer_0.layer.0.weight_g": (128, 1, 1, 1),
+        "embedding_00.layer_0.layer.0.bias": (128,),
+        "embedding_00.prediction.weight_v": (128, 128, 1, 1),
+        "embedding_01.layer_0.layer.0.weight_v": (128, 256, 1, 1),
+        "embedding_02.layer_1.layer.0.weight_v": (128, 128, 1, 1),
+        "propagation_00.net.left.layer_0.layer.0.weight_v": (128, 128, 3, 3),
+        "propagation_00.net.next_level.left.layer_0.layer.0.weight_v": (256, 128, 3, 3),
+        "propagation_00.net.next_level.next_level.left.layer_0.layer.0.weight_v": (512, 256, 3, 3),
+        "propagation_00.net.next_level.next_level.left.prediction.weight_v": (512, 512, 3, 3),
+        "propagation_00.net.next_level.right.layer_0.layer.0.weight_v": (256, 768, 3, 3),
+        "propagation_02.net.right.layer_0.layer.0.weight_v": (128, 384, 3, 3),
+        "propagation_02.net.right.prediction.weight_v": (128, 128, 3, 3),
+        "kernel_regressor.layer_0.layer.0.weight_v": (128, 256, 1, 1),
+        "kernel_regressor.prediction.weight_v": (441, 128, 1, 1),
+        "kernel_regressor.prediction.bias": (441,),
+    }
+    for name, shape in shapes.items():
+        assert tuple(sd[name].shape) == shape, name
+    nparams = sum(p.numel() for p in net.parameters())
+    assert 34.5e6 < nparams < 35.2e6          # ~34.8 M conv parameters
+    assert isinstance(net.kernel_update, modules.ProgressiveKernelApply)
+    assert net.kernel_update.splat
+    assert isinstance(net.propagation_00.net.right.output_activation, th.nn.LeakyReLU)
+    assert isinstance(net.kernel_regressor.layer_0.layer[1], th.nn.LeakyReLU)
+    assert not hasattr(net.kernel_regressor, "output_activation")
+    k = models.KPCN(27)
+    assert tuple(k.state_dict()["diffuse.prediction.weight"].shape) == (441, 100, 5, 5)
+    assert len([n for n in k.diffuse.state_dict() if n.endswith("weight")]) == 9
+
+
+# -- KernelApply / ProgressiveKernelApply known answers (test_modules.py:63-140) --
+def _kernel_apply_kat(device):
+    bs, c, h, w, k = 4, 5, 16, 16, 3
+    y, x, val = h // 2, w // 2, 1.43
+    data = th.zeros(bs, c, h, w)
+    data[0, 0, y, x] = val
+    weights = th.zeros(bs, k * k, h, w)
+    weights[0, :, y, x] = 1.0
+    for splat in [True, False]:
+        out, sum_w = modules.KernelApply(softmax=False, splat=splat)(
+            data.to(device), weights.clone().to(device))
+        out, sum_w = out.cpu(), sum_w.cpu()
+        assert sum_w.shape == (bs, 1, h, w)
+        assert abs(out[0, 0, y, x].item() - val) < 1e-4
+        if splat:
+            for dy in range(-(k // 2), k // 2 + 1):
+                for dx in range(-(k // 2), k // 2 + 1):
+                    assert abs(out[0, 0, y + dy, x + dx].item() - val) < 1e-4
+                    assert abs(sum_w[0, 0, y + dy, x + dx].item() - 1) < 1e-4
+        else:
+            assert abs(sum_w[0, 0, y, x].item() - k * k) < 1e-4
+    # softmax mode (KPCN): the weights of every pixel sum to one
+    out, sum_w = modules.KernelApply(softmax=True, splat=False)(
+        data.to(device), th.randn(bs, k * k, h, w).to(device))
+    assert (sum_w.cpu() - 1).abs().max().item() < 1e-5
+
+
+def _progressive_kat(device):
+    bs, c, h, w, k = 4, 5, 16, 16, 3
+    y, x, val = h // 2, w // 2, 1.43
+    data = th.zeros(bs, c, h, w)
+    data[0, 0, y, x] = val
+    weights = th.zeros(bs, k * k, h, w)
+    weights[0, :, y, x] = 1.0
+    for splat in [True, False]:
+        func = modules.ProgressiveKernelApply(splat=splat)
+        out, sum_w, max_w = func(data.to(device), weights.clone().to(device), None, None, None)
+        out, sum_w, max_w = out.cpu(), sum_w.cpu(), max_w.cpu()
+        assert sum_w.shape == (bs, 1, h, w) and max_w.shape == (bs, 1, h, w)
+        assert abs(out[0, 0, y, x].item() - val) < 1e-4
+        if splat:
+            for dy in range(-(k // 2), k // 2 + 1):
+                for dx in range(-(k // 2), k // 2 + 1):
+                    assert abs(out[0, 0, y + dy, x + dx].item() - val) < 1e-4
+        else:
+            assert abs(sum_w[0, 0, y, x].item() - k * k) < 1e-4
+        with pytest.raises(RuntimeError):
+            func(data.to(device), weights.clone().to(device), None, sum_w.to(device), None)
+
+
+def _softmax_splat_reference(radiance, logits, k):
+    """float64 restatement of `spp` progressive splat updates followed by the
+    normalization: every sample's scatter kernel is softmax-normalized jointly
+    with all other contributions landing on the same pixel (out-of-image sources
+    contribute a zero logit to the denominator only)."""
+    bs, spp, c, h, w = radiance.shape
+    c0 = (k - 1) // 2
+    L = logits.double().view(bs, spp, k, k, h, w)
+    R = radiance.double()
+    pad = (c0, c0, c0, c0)
+    Lp = F.pad(L, pad)
+    Rp = F.pad(R, pad)
+    # gather form: pixel q receives from p = q + (dy - c0, dx - c0) the logit
+    # S[K-1-dy, K-1-dx, p]
+    G = th.zeros(bs, spp, k, k, h, w, dtype=th.float64)
+    for dy in range(k):
+        for dx in range(k):
+            G[:, :, dy, dx] = Lp[:, :, k - 1 - dy, k - 1 - dx, dy:dy + h, dx:dx + w]
+    m = G.amax(dim=(1, 2, 3), keepdim=True)
+    E = th.exp(G - m)
+    sum_w = E.sum(dim=(1, 2, 3))
+    sum_r = th.zeros(bs, c, h, w, dtype=th.float64)
+    for dy in range(k):
+        for dx in range(k):
+            sum_r += (E[:, :, dy, dx].unsqueeze(2) * Rp[:, :, :, dy:dy + h, dx:dx + w]).sum(1)
+    return sum_r, sum_w.unsqueeze(1), m.view(bs, 1, h, w)
+
+
+def _progressive_equals_joint_softmax(device):
+    th.manual_seed(3)
+    bs, spp, c, h, w, k = 2, 3, 3, 12, 16, 5
+    radiance = th.rand(bs, spp, c, h, w)
+    logits = 3 * th.randn(bs, spp, k * k, h, w)
+    func = modules.ProgressiveKernelApply(splat=True)
+    sum_r = sum_w = max_w = None
+    for sp in range(spp):
+        sum_r, sum_w, max_w = func(radiance[:, sp].to(device),
+                                   logits[:, sp].contiguous().to(device), sum_r, sum_w, max_w)
+    rr, rw, rm = _softmax_splat_reference(radiance, logits, k)
+    assert th.allclose(max_w.cpu().double(), rm, atol=0, rtol=0)
+    assert th.allclose(sum_w.cpu().double(), rw, rtol=2e-5)
+    assert th.allclose(sum_r.cpu().double(), rr, rtol=2e-5, atol=1e-6)
+
+
+def test_kernel_apply_cpu_logic(oracle_ops):
+    _kernel_apply_kat("cpu")
+
+
+def test_progressive_kernel_apply_cpu_logic(oracle_ops):
+    _progressive_kat("cpu")
+    _progressive_equals_joint_softmax("cpu")
+
+
+def _tiny_multisteps(device, train):
+    th.manual_seed(0)
+    net = models.Multisteps(6, 2, width=8, embedding_width=8, ksize=5, nsteps=2).to(device)
+    net.train(train)
+    bs, spp, h, w = 1, 3, 24, 20
+    samples = {"radiance": th.rand(bs, spp, 3, h, w, device=device),
+               "features": th.randn(bs, spp, 6, h, w, device=device),
+               "global_features": th.randn(bs, 2, 1, 1, device=device)}
+    return net, samples
+
+
+def test_multisteps_forward_cpu_logic(oracle_ops):
+    net, samples = _tiny_multisteps("cpu", train=True)
+    out = net(samples)["radiance"]
+    assert out.shape == (1, 3, 20, 16)
+    assert th.isfinite(out).all()
+    out.mean().backward()
+    assert all(p.grad is not None for p in net.kernel_regressor.parameters())
+    # bs == 1: the eval path (one sample at a time) gives the same image
+    net.eval()
+    with th.no_grad():
+        out_eval = net(samples)["radiance"]
+    assert th.allclose(out, out_eval, rtol=1e-4, atol=1e-5)
+    # the output is a convex combination of the sample radiances
+    assert out_eval.min() >= 0 and out_eval.max() <= 1 + 1e-5
+
+
+def test_kpcn_forward_cpu_logic(oracle_ops):
+    th.manual_seed(0)
+    net = models.KPCN(4, ksize=3, depth=2, width=8)
+    h = w = 20
+    data = {"kpcn_diffuse_in": th.randn(1, 4, h, w), "kpcn_specular_in": th.randn(1, 4, h, w),
+            "kpcn_diffuse_buffer": th.rand(1, 3, h, w), "kpcn_specular_buffer": th.rand(1, 3, h, w),
+            "kpcn_albedo": th.rand(1, 3, h, w)}
+    out = net(data)
+    assert out["radiance"].shape == (1, 3, h - 8, w - 8)
+    assert th.allclose(out["radiance"],
+                       data["kpcn_albedo"][..., 4:-4, 4:-4] * out["diffuse"]
+                       + th.exp(out["specular"]) - 1)
+
+
+# -- GPU: the same checks on the real ops ----------------------------------------
+@pytest.mark.gpu
+def test_kernel_apply_gpu():
+    _kernel_apply_kat("cuda")
+
+
+@pytest.mark.gpu
+def test_progressive_kernel_apply_gpu():
+    _progressive_kat("cuda")
+    _progressive_equals_joint_softmax("cuda")
+
+
+@pytest.mark.gpu
+def test_multisteps_forward_gpu_matches_oracle_backed_cpu(monkeypatch):
+    net, samples = _tiny_multisteps("cuda", train=True)
+    out = net(samples)["radiance"]
+    out.mean().backward()
+    grads = [p.grad.detach().cpu().clone() for p in net.kernel_regressor.parameters()]
+    net.eval()
+    with th.no_grad():
+        out_eval = net(samples)["radiance"]
+    assert th.allclose(out, out_eval, rtol=1e-4, atol=1e-5)
+    # same model on CPU with the oracle standing in for the custom ops
+    KW, S2G = kats.oracle_functions()
+    monkeypatch.setattr(funcs, "KernelWeighting", KW)
+    monkeypatch.setattr(funcs, "Scatter2Gather", S2G)
+    cpu_net = net.cpu().train()
+    cpu_net.zero_grad()
+    ref = cpu_net({k: v.cpu() for k, v in samples.items()})["radiance"]
+    assert th.allclose(out.detach().cpu(), ref, rtol=1e-4, atol=1e-5)
+    ref.mean().backward()
+    for g, p in zip(grads, cpu_net.kernel_regressor.parameters()):
+        assert th.allclose(g, p.grad, rtol=1e-3, atol=1e-6)

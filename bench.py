@@ -301,9 +301,15 @@ def run_b200(a):
     roofline = None
     if table:
         top = max(table, key=lambda n: table[n]["avg_ms"] * table[n]["launches"])
+        traffic = None
+        if (B, C, H, W, K) == (4, 3, 720, 1280, 21):     # the shape ncu captured
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[top]["bytes"]
+            except (OSError, ValueError, KeyError):
+                pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": table[top]["GB/s"],
                     "peak": peak, "unit": "GB/s", "frac": table[top]["frac"],
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": per_sample[top] * launch_samples,
                     "step_frac": 4 * (2 * K * K + K * K + 5 * C + 2) * samples_step / world
                     / (ms_step * 1e-3) / 1e9 / peak,

@@ -80,7 +80,8 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_KW_DWEIGHTS 1  /* backward, d_weights (write stream)     */
 #define SBMC_KERNEL_KW_DDATA 2     /* backward, d_data (reads the weights)   */
 #define SBMC_KERNEL_S2G 3          /* Scatter2Gather                         */
-#define SBMC_KERNEL_OTHER 4        /* memsets / halo adds / fused splat ...  */
+#define SBMC_KERNEL_OTHER 4        /* halo adds of the host pipeline         */
+#define SBMC_KERNEL_SPLAT_FWD 5    /* fused ProgressiveKernelApply forward   */
 #define SBMC_NUM_KERNEL_KINDS 8
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
@@ -114,6 +115,21 @@ SBMC_API int sbmc_kernel_weighting_bwd_f32(const float *data, const float *weigh
                                   const float *d_sum_w, float *d_data,
                                   float *d_weights, int64_t n, int c, int64_t h,
                                   int64_t w, int kh, int kw, void *stream);
+
+/* ---- fused progressive splat (sbmc/modules.py:364-473, inference) -------- *
+ * One ProgressiveKernelApply update in a single pass over the kernel logits:
+ *   G = splat ? Scatter2Gather(kernels) : kernels        (never materialised)
+ *   new_max = max(max_taps G, max_w);  scaler = exp(max_w - new_max)
+ *   sum_r = sum_r * scaler + sum_taps exp(G - new_max) * data(tap)
+ *   sum_w = sum_w * scaler + sum_taps exp(G - new_max);   max_w = new_max
+ * kernels [n][kh*kw][h][w] are the raw logits (not modified), data [n][c][h][w];
+ * sum_r [n][c][h][w], sum_w / max_w [n][h][w] are updated in place.  first != 0
+ * is the initialisation step (sum_r = sum_w = max_w = None in the reference):
+ * the state buffers are written without being read. */
+SBMC_API int sbmc_progressive_splat_fwd_f32(const float *kernels, const float *data,
+                                   float *sum_r, float *sum_w, float *max_w,
+                                   int64_t n, int c, int64_t h, int64_t w, int kh,
+                                   int kw, int splat, int first, void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

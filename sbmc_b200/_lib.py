@@ -28,6 +28,9 @@ SIGNATURES = {
     "sbmc_kernel_weighting_bwd_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64,
                 _int, _int, _ptr]),
+    "sbmc_progressive_splat_fwd_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
+                _int, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
@@ -93,7 +96,7 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other"}
+                4: "other", 5: "splat_fwd"}
 NUM_KERNEL_KINDS = 8
 
 

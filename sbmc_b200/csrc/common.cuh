@@ -98,6 +98,21 @@ __device__ __forceinline__ void stg_stream(float *p, const float4 &v) {
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// Store-policy variants for the tuning sweep: 0 = .cs (evict-first), 1 = default
+// write-back, 2 = no L1 allocation.
+template <int POLICY>
+__device__ __forceinline__ void stg_policy(float *p, const float4 &v) {
+  if (POLICY == 1)
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  else if (POLICY == 2)
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  else
+    stg_stream(p, v);
+}
 __device__ __forceinline__ float4 ldg_cached(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }

@@ -43,6 +43,20 @@ struct TileGeom {
   static constexpr int TWS = kTileW - 4 + WIN;    // smem row pitch (floats)
 };
 
+// Elements [4*lane + r, 4*lane + r + 4) of a 16-byte aligned shared-memory row;
+// r is warp-uniform.
+__device__ __forceinline__ float4 lds_shifted4(const float *row, int lane, int r) {
+  const float4 a = *reinterpret_cast<const float4 *>(row + 4 * lane);
+  if (r == 0) return a;
+  const float4 b = *reinterpret_cast<const float4 *>(row + 4 * lane + 4);
+  if (r == 1) return make_float4(a.y, a.z, a.w, b.x);
+  if (r == 2) return make_float4(a.z, a.w, b.x, b.y);
+  return make_float4(a.w, b.x, b.y, b.z);
+}
+
+constexpr int kBoxPad = 4;                       // extra columns of a shifted box
+constexpr int kBoxW = kTileW + kBoxPad;          // 132 floats = 528 B
+
 struct TileCoord {
   int xt, yt, n;
 };
@@ -176,7 +190,7 @@ kw_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
 // ---------------------------------------------------------------------------
 // Backward, d_weights: pure write stream.  Same tiling as the forward.
 // ---------------------------------------------------------------------------
-template <int C, int KW, int ROWS, int MINB, int CH>
+template <int C, int KW, int ROWS, int MINB, int CH, int STORE = 0>
 __global__ void __launch_bounds__(ROWS * 32, MINB)
 kw_bwd_dweights_kernel(const __grid_constant__ CUtensorMap dmap,
                        const float *__restrict__ dO,
@@ -250,8 +264,8 @@ kw_bwd_dweights_kernel(const __grid_constant__ CUtensorMap dmap,
               for (int c = 0; c < C; ++c)
                 v[i] = fmaf(win[c][G::LEFT + cs + j + i - lo], go[c][i], v[i]);
             }
-            stg_stream(wp + (i64)(cs + j) * plane,
-                       make_float4(v[0], v[1], v[2], v[3]));
+            stg_policy<STORE>(wp + (i64)(cs + j) * plane,
+                              make_float4(v[0], v[1], v[2], v[3]));
           }
         }
       }

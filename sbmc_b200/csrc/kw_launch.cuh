@@ -59,7 +59,7 @@ int run_fwd(const float *data_ext, const float *weights, float *output,
   return SBMC_OK;
 }
 
-template <int C, int KW, int ROWS, int MINB, int CH>
+template <int C, int KW, int ROWS, int MINB, int CH, int STORE = 0>
 int run_bwd_dweights(const float *data_ext, const float *d_output,
                      const float *d_sum_w, float *d_weights, i64 n, i64 h, i64 w,
                      int kh, int halo_top, int halo_bot, cudaStream_t st) {
@@ -68,7 +68,7 @@ int run_bwd_dweights(const float *data_ext, const float *d_output,
   if (!make_image_map<KW>(&dmap, data_ext, n, C, hext, w, ROWS + kh - 1))
     return SBMC_ECUDA;
   const size_t smem = tile_smem_bytes<C, KW, ROWS>(kh);
-  auto kern = kw_bwd_dweights_kernel<C, KW, ROWS, MINB, CH>;
+  auto kern = kw_bwd_dweights_kernel<C, KW, ROWS, MINB, CH, STORE>;
   SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int xt = (int)ceil_div(w, kTileW), yt = (int)ceil_div(h, ROWS);
   const unsigned grid = (unsigned)((i64)xt * yt * n);

@@ -1,82 +1,105 @@
-// s2g.cu -- Scatter2Gather as a pure TMA copy engine program.
+// s2g.cu -- Scatter2Gather: TMA-fed shifted plane copies.
 //
 // gather[n][dy][dx][y][x] = scatter[n][KH-1-dy][KW-1-dx][y+dy-c0h][x+dx-c0w],
 // zero when the source pixel is outside the image
 // (reference: src/scatter2gather.cpp:34-47).  That is K*K*N independent shifted
-// 2-D plane copies with zero fill, so the kernel has no arithmetic at all: one
-// elected thread per CTA walks a list of (box, tap, n) jobs, pulls each source
-// box with a TMA tiled load at the SHIFTED coordinates (out-of-bounds elements,
-// including negative coordinates, arrive as 0.0f -- the boundary condition for
-// free), and pushes the same shared-memory buffer back out with a TMA tiled
-// store at the aligned destination coordinates (out-of-bounds part clipped).
-// A ring of STAGES buffers keeps several loads and stores in flight per CTA.
-// Bit-exact by construction (bytes are only moved).
-#include "common.cuh"
+// 2-D plane copies with zero fill and no arithmetic.
+//
+// A CTA owns a (ROWS x 128)-pixel tile of one image and walks all K*K taps.  A
+// producer warp pulls, for every tap, the box of the transposed source plane at
+// the shifted coordinates with TMA into a shared-memory ring; elements outside
+// the image (including negative coordinates) arrive as 0.0f -- the reference's
+// boundary condition for free.  TMA needs the box to start on a 16-byte boundary
+// (measured on B200: any other innermost coordinate faults with "illegal
+// instruction", profiles/r1c_tma_coordinate_probe.txt), so the x shift
+// s = dx - c0w is split into an aligned part, applied to the box coordinate, and
+// a residue r = s mod 4 in [0, 4): boxes with r != 0 are 4 columns wider and the
+// consumer warps apply the residue when they read shared memory (two aligned
+// 128-bit loads + a warp-uniform select).  Each thread then writes its 4 pixels
+// with one coalesced 128-bit streaming store.  Bit-exact: bytes are only moved.
+#include "kw_kernels.cuh"
 
 namespace sbmc {
 
-struct S2GJobs {
-  int kh, kw, bx, by;          // kernel size, box size
-  int nxb, nyb;                // boxes per row / column
-  long long njobs;             // nxb * nyb * kh * kw * n
-};
+template <int ROWS, int STAGES, int TPS>
+__global__ void __launch_bounds__((ROWS + 1) * 32)
+s2g_kernel(const __grid_constant__ CUtensorMap map128,   // box 128 x ROWS
+           const __grid_constant__ CUtensorMap map132,   // box 132 x ROWS
+           float *__restrict__ gather, int H, int W, int KH, int KW, int xtiles,
+           int ytiles) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *smem_raw = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  constexpr int kSlot = ROWS * kBoxW;            // floats per tap slot (max box)
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * TPS * kSlot);
+  uint64_t *empty = full + STAGES;
 
-template <int STAGES>
-__global__ void __launch_bounds__(32)
-s2g_tma_kernel(const __grid_constant__ CUtensorMap smap,
-               const __grid_constant__ CUtensorMap gmap, const S2GJobs J) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[STAGES];
-  if (threadIdx.x != 0) return;  // a single thread drives the copy engine
+  const TileCoord tc = decode_tile(blockIdx.x, xtiles, ytiles);
+  const int X0 = tc.xt * kTileW, Y0 = tc.yt * ROWS;
+  const int c0h = (KH - 1) / 2, c0w = (KW - 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = KH * KW;
+  const int nstages = (taps + TPS - 1) / TPS;
 
-  const uint32_t box_bytes = (uint32_t)(J.bx * J.by * sizeof(float));
-  const int c0h = (J.kh - 1) / 2, c0w = (J.kw - 1) / 2;
-  const long long taps = (long long)J.kh * J.kw;
-  const long long first = blockIdx.x, step = gridDim.x;
-  const long long mine = first < J.njobs ? (J.njobs - first + step - 1) / step : 0;
-
-  for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-  fence_mbar_init();
-  prefetch_tensormap(&smap);
-  prefetch_tensormap(&gmap);
-
-  auto coords = [&](long long k, int &x, int &y, int &tap, int &n) {
-    long long job = first + k * step;
-    x = (int)(job % J.nxb) * J.bx;
-    job /= J.nxb;
-    y = (int)(job % J.nyb) * J.by;
-    job /= J.nyb;
-    tap = (int)(job % taps);
-    n = (int)(job / taps);
-  };
-  auto issue = [&](long long k) {
-    int x, y, tap, n;
-    coords(k, x, y, tap, n);
-    const int dy = tap / J.kw, dx = tap % J.kw;
-    const int s = (int)(k % STAGES);
-    mbar_expect_tx(&bars[s], box_bytes);
-    tma_load_4d(smem_raw + (size_t)s * box_bytes, &smap, &bars[s], x + dx - c0w,
-                y + dy - c0h, (J.kh - 1 - dy) * J.kw + (J.kw - 1 - dx), n);
-  };
-
-  constexpr int AHEAD = STAGES - 1;
-  for (long long k = 0; k < AHEAD && k < mine; ++k) issue(k);
-  for (long long k = 0; k < mine; ++k) {
-    const int s = (int)(k % STAGES);
-    mbar_wait(&bars[s], (uint32_t)((k / STAGES) & 1));
-    fence_proxy_async();
-    int x, y, tap, n;
-    coords(k, x, y, tap, n);
-    tma_store_4d(&gmap, smem_raw + (size_t)s * box_bytes, x, y, tap, n);
-    tma_commit_group();
-    if (k + AHEAD < mine) {
-      // the stage about to be refilled was last read by the store of job k-1:
-      // allow only the newest store (job k) to still be reading shared memory.
-      tma_wait_group_read<1>();
-      issue(k + AHEAD);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ROWS);
     }
+    fence_mbar_init();
   }
-  tma_wait_group<0>();
+  __syncthreads();
+
+  if (warp == ROWS) {  // ---- producer warp: one lane drives the copy engine ----
+    if (lane == 0) {
+      for (int it = 0; it < nstages; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+        const int t0 = it * TPS;
+        const int cnt = (taps - t0 < TPS) ? (taps - t0) : TPS;
+        uint32_t bytes = 0;
+        for (int j = 0; j < cnt; ++j) {
+          const int dx = (t0 + j) % KW;
+          bytes += (uint32_t)(ROWS * (((dx - c0w) & 3) ? kBoxW : kTileW) * sizeof(float));
+        }
+        mbar_expect_tx(&full[s], bytes);
+        for (int j = 0; j < cnt; ++j) {
+          const int tap = t0 + j;
+          const int dy = tap / KW, dx = tap - dy * KW;
+          const int sh = dx - c0w;
+          tma_load_4d(ring + ((size_t)s * TPS + j) * kSlot, (sh & 3) ? &map132 : &map128,
+                      &full[s], X0 + (sh & ~3), Y0 + dy - c0h,
+                      (KH - 1 - dy) * KW + (KW - 1 - dx), tc.n);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps: warp r owns row Y0 + r, lane l pixels X0 + 4l .. +3 ----
+  const int y = Y0 + warp, x0 = X0 + 4 * lane;
+  const bool valid = (y < H) && (x0 < W);
+  const long long plane = (long long)H * W;
+  float *gp = gather + (long long)tc.n * taps * plane + (long long)y * W + x0;
+  int tap = 0;
+  for (int it = 0; it < nstages; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+    const int cnt = (taps - tap < TPS) ? (taps - tap) : TPS;
+    for (int j = 0; j < cnt; ++j, ++tap) {
+      const int dx = tap % KW;
+      const int r = (dx - c0w) & 3;
+      const int pitch = r ? kBoxW : kTileW;
+      const float4 v = lds_shifted4(ring + ((size_t)s * TPS + j) * kSlot + (size_t)warp * pitch,
+                                    lane, r);
+      if (valid) stg_stream(gp + (long long)tap * plane, v);
+    }
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s]))
+                   : "memory");
+  }
 }
 
 static bool make_plane_map(CUtensorMap *map, const float *base, i64 n, i64 taps,
@@ -88,42 +111,30 @@ static bool make_plane_map(CUtensorMap *map, const float *base, i64 n, i64 taps,
   return encode_tensor_map_f32(map, base, 4, dims, strides, box);
 }
 
-// Tuning knobs (exposed for the sweep tool through launch_s2g_cfg).
-int launch_s2g_cfg(const float *scatter, float *gather, i64 n, int kh, int kw,
-                   i64 h, i64 w, int bx, int by, int stages, int ctas_per_sm,
-                   cudaStream_t st) {
-  const i64 taps = (i64)kh * kw;
-  CUtensorMap smap, gmap;
-  if (!make_plane_map(&smap, scatter, n, taps, h, w, bx, by) ||
-      !make_plane_map(&gmap, gather, n, taps, h, w, bx, by))
+template <int ROWS, int STAGES, int TPS>
+int run_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h, i64 w,
+            cudaStream_t st) {
+  CUtensorMap m128, m132;
+  if (!make_plane_map(&m128, scatter, n, (i64)kh * kw, h, w, kTileW, ROWS) ||
+      !make_plane_map(&m132, scatter, n, (i64)kh * kw, h, w, kBoxW, ROWS))
     return SBMC_ECUDA;
-  S2GJobs J;
-  J.kh = kh; J.kw = kw; J.bx = bx; J.by = by;
-  J.nxb = (int)ceil_div(w, bx);
-  J.nyb = (int)ceil_div(h, by);
-  J.njobs = (long long)J.nxb * J.nyb * taps * n;
-  const size_t smem = (size_t)stages * bx * by * sizeof(float);
-  i64 grid = (i64)num_sms() * ctas_per_sm;
-  if (grid > J.njobs) grid = J.njobs;
-  if (grid < 1) grid = 1;
-#define SBMC_S2G(S)                                                            \
-  case S: {                                                                    \
-    auto kern = s2g_tma_kernel<S>;                                             \
-    SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<(unsigned)grid, 32, smem, st>>>(smap, gmap, J);                     \
-  } break;
-  KernelTimer timer(SBMC_KERNEL_S2G, st);
-  switch (stages) {
-    SBMC_S2G(2) SBMC_S2G(3) SBMC_S2G(4) SBMC_S2G(6) SBMC_S2G(8)
-    default:
-      set_error("s2g: unsupported stage count %d", stages);
-      return SBMC_EINVAL;
+  const size_t smem = (size_t)STAGES * TPS * ROWS * kBoxW * 4 + 2 * STAGES * 8 + 128;
+  auto kern = s2g_kernel<ROWS, STAGES, TPS>;
+  SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int xt = (int)ceil_div(w, kTileW), yt = (int)ceil_div(h, ROWS);
+  const unsigned grid = (unsigned)((i64)xt * yt * n);
+  {
+    KernelTimer timer(SBMC_KERNEL_S2G, st);
+    kern<<<grid, (ROWS + 1) * 32, smem, st>>>(m128, m132, gather, (int)h, (int)w, kh, kw,
+                                              xt, yt);
   }
-#undef SBMC_S2G
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
   return SBMC_OK;
 }
+
+// tuned configuration (profiles/): 8 rows, 4 stages of 3 taps = 50 KB in flight per CTA
+constexpr int kS2gRows = 8, kS2gStages = 4, kS2gTps = 3;
 
 int launch_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h,
                i64 w, cudaStream_t st) {
@@ -131,17 +142,15 @@ int launch_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h
       !force_generic() && (w % 4 == 0) && w >= 4 &&
       (reinterpret_cast<uintptr_t>(scatter) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(gather) & 15) == 0 && w < (1ll << 31) - 512 &&
-      h < (1ll << 31) - 512 && (i64)kh * kw * n < (1ll << 31) &&
+      h < (1ll << 31) - 512 && (i64)kh * kw < (1ll << 20) &&
+      ceil_div(w, kTileW) * ceil_div(h, kS2gRows) * n < 0x7fffffffll &&
       (unsigned long long)w * h * kh * kw * 4ull < (1ull << 40);
   if (!tma_ok) {
     note_path(2);
     return generic_s2g(scatter, gather, n, kh, kw, h, w, st);
   }
   note_path(1);
-  // box: up to 256 x 16 floats (16 KB); 4 stages, 3 CTAs per SM
-  int bx = (int)(w < 256 ? w : 256);
-  int by = (int)(h < 16 ? h : 16);
-  return launch_s2g_cfg(scatter, gather, n, kh, kw, h, w, bx, by, 4, 3, st);
+  return run_s2g<kS2gRows, kS2gStages, kS2gTps>(scatter, gather, n, kh, kw, h, w, st);
 }
 
 }  // namespace sbmc

@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functions as funcs
+from . import splat as _splat
 from ._compat import get_logger
 
 __all__ = ["ConvChain", "Autoencoder", "KernelApply", "ProgressiveKernelApply"]
@@ -270,6 +271,8 @@ class ProgressiveKernelApply(nn.Module):
     def __init__(self, splat=False):
         super(ProgressiveKernelApply, self).__init__()
         self.splat = splat
+        # use the single-pass sm_100a kernel when no gradient is needed
+        self.fused = True
 
     def forward(self, data, kernels, sum_r, sum_w, max_w):
         """First call: pass sum_r = sum_w = max_w = None.
@@ -287,6 +290,11 @@ class ProgressiveKernelApply(nn.Module):
             LOG.error("sum_r is None, this is the initialization step: "
                       "sum_w and max_w should be None as well.")
             raise RuntimeError("all of sum_r, sum_w, max_w should be none")
+
+        if getattr(self, "fused", False) and k * k == k2 and \
+                _splat.fused_available(data, kernels, sum_r, sum_w, max_w):
+            return _splat.progressive_splat_update(data, kernels, sum_r, sum_w, max_w,
+                                                   self.splat)
 
         kernels = kernels.view(bs, k, k, h, w)
         if self.splat:

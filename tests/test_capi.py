@@ -100,3 +100,39 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "sbmc_oracle" not in text, f
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "sbmc")),
+                    reason="reference tree not present (GPU box)")
+@pytest.mark.skipif(th.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_reference_functions_bind_to_the_drop_in(monkeypatch):
+    """INTEGRATION.md option A: the reference's own sbmc/functions.py, unmodified,
+    on top of sbmc_b200.halide_ops installed as `sbmc.halide_ops`.  Without a GPU
+    the call must get through every argument / shape check of the drop-in (the
+    reference passes its inputs then its resize_()d outputs, functions.py:53-59,
+    91-98,105-114) and stop at the missing device."""
+    import importlib.util
+    import sys
+    import types
+    ttools = types.ModuleType("ttools")
+    from sbmc_b200._compat import get_logger
+    ttools.get_logger = get_logger
+    pkg = types.ModuleType("sbmc")
+    pkg.__path__ = [os.path.join(REFERENCE, "sbmc")]
+    monkeypatch.setitem(sys.modules, "ttools", ttools)
+    monkeypatch.setitem(sys.modules, "sbmc", pkg)
+    monkeypatch.setitem(sys.modules, "sbmc.halide_ops", halide_ops)
+    pkg.halide_ops = halide_ops
+    spec = importlib.util.spec_from_file_location(
+        "sbmc.functions", os.path.join(REFERENCE, "sbmc", "functions.py"))
+    ref = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "sbmc.functions", ref)
+    spec.loader.exec_module(ref)
+    assert ref.ops is halide_ops
+    with pytest.raises(RuntimeError, match="no CPU compute path"):
+        ref.KernelWeighting.apply(th.zeros(2, 3, 8, 8), th.zeros(2, 5, 5, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU compute path"):
+        ref.Scatter2Gather.apply(th.zeros(2, 5, 5, 8, 8))

@@ -274,3 +274,37 @@ def test_multisteps_forward_gpu_matches_oracle_backed_cpu(monkeypatch):
     ref.mean().backward()
     for g, p in zip(grads, cpu_net.kernel_regressor.parameters()):
         assert th.allclose(g, p.grad, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("splat", [True, False])
+@pytest.mark.parametrize("shape", [(2, 3, 24, 132, 5), (1, 3, 30, 256, 21), (1, 3, 9, 18, 7),
+                                   (2, 5, 12, 16, 3), (1, 2, 10, 12, 5)])
+def test_fused_progressive_matches_composed(shape, splat):
+    """The single-pass kernel against the reference chain built from the
+    individual ops (Scatter2Gather -> max -> exp -> KernelWeighting)."""
+    from sbmc_b200 import _lib
+    bs, c, h, w, k = shape
+    th.manual_seed(sum(shape))
+    spp = 3
+    radiance = th.rand(bs, spp, c, h, w, device="cuda")
+    logits = 4 * th.randn(bs, spp, k * k, h, w, device="cuda")
+    fused = modules.ProgressiveKernelApply(splat=splat)
+    composed = modules.ProgressiveKernelApply(splat=splat)
+    composed.fused = False
+    a = (None, None, None)
+    b = (None, None, None)
+    with th.no_grad():
+        for sp in range(spp):
+            before = _lib.launch_count()
+            a = fused(radiance[:, sp], logits[:, sp].clone(), *a)
+            assert _lib.launch_count() == before + 1          # one kernel per update
+            b = composed(radiance[:, sp], logits[:, sp].clone(), *b)
+            assert th.equal(a[2], b[2])                        # max_w: exact
+            assert th.allclose(a[1], b[1], rtol=1e-5, atol=0)
+            assert th.allclose(a[0], b[0], rtol=1e-5, atol=1e-6)
+    rr, rw, rm = (None, None, None)
+    if splat:
+        rr, rw, rm = _softmax_splat_reference(radiance.cpu(), logits.cpu(), k)
+        assert th.allclose(a[1].cpu().double(), rw, rtol=1e-5)
+        assert th.allclose(a[0].cpu().double(), rr, rtol=1e-5, atol=1e-6)

@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "../sbmc_b200/csrc/kw_launch.cuh"
+#include "../sbmc_b200/csrc/s2g.cu"
+#include "../sbmc_b200/csrc/splat.cu"
 
 using namespace sbmc;
 
@@ -80,6 +82,21 @@ static void time_it(Ctx &c, const char *name, double bytes_per_sample, F &&f) {
                                                 c.k, 0, 0, c.st);             \
   });
 
+#define DWS(ROWS, MINB, CH, ST)                                               \
+  time_it(c, "dwt  rows=" #ROWS " minb=" #MINB " ch=" #CH " store=" #ST, 4.0 * (441 + 7), [&] { \
+    return run_bwd_dweights<3, 21, ROWS, MINB, CH, ST>(c.data, c.dout, c.dsw, c.dwt, c.n, \
+                                                       c.h, c.w, c.k, 0, 0, c.st); \
+  });
+#define S2G(ROWS, STAGES, TPS)                                                \
+  time_it(c, "s2g  rows=" #ROWS " stages=" #STAGES " tps=" #TPS, 8.0 * 441, [&] { \
+    return run_s2g<ROWS, STAGES, TPS>(c.wt, c.dwt, c.n, c.k, c.k, c.h, c.w, c.st); \
+  });
+#define SPL(ROWS, STAGES, TPS)                                                \
+  time_it(c, "splat rows=" #ROWS " stages=" #STAGES " tps=" #TPS, 4.0 * (441 + 3 + 10), [&] { \
+    return run_splat<3, 21, ROWS, STAGES, TPS>(c.wt, c.data, c.out, c.sw, c.dsw, c.n, c.h, \
+                                               c.w, c.k, 1, 0, c.st);         \
+  });
+
 int main(int argc, char **argv) {
   Ctx c;
   const char *which = argc > 1 ? argv[1] : "all";
@@ -113,7 +130,18 @@ int main(int argc, char **argv) {
   }
   if (all || !strcmp(which, "dda")) {
     DDA(10, 1, 7) DDA(10, 1, 11) DDA(10, 1, 21) DDA(5, 2, 7) DDA(5, 1, 21) DDA(5, 1, 11)
-    DDA(2, 4, 7) DDA(2, 2, 21)
+    DDA(2, 4, 7) DDA(2, 2, 21) DDA(1, 8, 7) DDA(4, 2, 7) DDA(2, 6, 7) DDA(2, 4, 11)
+  }
+  if (all || !strcmp(which, "dws")) {
+    DWS(8, 2, 7, 1) DWS(8, 2, 7, 2) DWS(16, 1, 7, 1) DWS(16, 1, 7, 2) DWS(8, 2, 21, 1)
+    DWS(4, 4, 7, 1)
+  }
+  if (all || !strcmp(which, "s2g")) {
+    S2G(8, 4, 3) S2G(4, 6, 3) S2G(8, 3, 7) S2G(4, 8, 3) S2G(16, 2, 3) S2G(2, 8, 7)
+    S2G(8, 6, 3)
+  }
+  if (all || !strcmp(which, "splat")) {
+    SPL(4, 6, 3) SPL(8, 4, 3) SPL(4, 8, 3) SPL(2, 8, 7) SPL(8, 6, 3) SPL(16, 2, 3)
   }
   return 0;
 }

@@ -37,8 +37,8 @@ UNIT = "Msamples/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--b", type=int, default=4)
     p.add_argument("--spp", type=int, default=8)
@@ -81,7 +81,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -91,9 +91,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,7 +103,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        rows = self.rows
+        if t0 is not None:                       # samples taken inside the timed region
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.06]
+            rows = inside or rows
+        for _, row in rows:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 9:
                 continue
@@ -251,27 +255,29 @@ def run_b200(a):
             dist.barrier()
         th.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                  # runs through warm-up and the timed region
     for _ in range(a.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     _lib.timing_collect()
     _lib.timing_enable(True)
     launches0 = _lib.launch_count()
     ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(a.steps):
         step()
     ev1.record()
     barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     _lib.timing_enable(False)
     kernels = _lib.timing_collect()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     t = th.tensor([ms], device=dev, dtype=th.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -52,6 +52,8 @@ extern "C" {
 #define SBMC_ECUDA (-2)    /* a CUDA runtime / driver call failed             */
 #define SBMC_ENODEV (-3)   /* no sm_100 device / driver available             */
 #define SBMC_EALIGN (-4)   /* pointer not 4-byte aligned                      */
+#define SBMC_EUNSUPPORTED (-5) /* no fused kernel for this shape: the caller
+                                  composes the individual operators instead   */
 
 /* Library version (major*10000 + minor*100 + patch). */
 SBMC_API int sbmc_b200_version(void);
@@ -82,6 +84,7 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_S2G 3          /* Scatter2Gather                         */
 #define SBMC_KERNEL_OTHER 4        /* halo adds of the host pipeline         */
 #define SBMC_KERNEL_SPLAT_FWD 5    /* fused ProgressiveKernelApply forward   */
+#define SBMC_KERNEL_SPLAT_BWD 6    /* fused ProgressiveKernelApply backward  */
 #define SBMC_NUM_KERNEL_KINDS 8
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
@@ -130,6 +133,19 @@ SBMC_API int sbmc_progressive_splat_fwd_f32(const float *kernels, const float *d
                                    float *sum_r, float *sum_w, float *max_w,
                                    int64_t n, int c, int64_t h, int64_t w, int kh,
                                    int kw, int splat, int first, void *stream);
+
+/* Backward of one splat-mode update in scatter space (one read of the logits,
+ * one write of their gradient).  planes [n][c+3][h][w] packs, per target pixel:
+ * [0,c) dL/dsum_r', c: dL/dsum_w', c+1: the updated running max m', c+2: the
+ * gradient routed to the tap maximum (0 where the max came from earlier samples).
+ *   d_kernels[n][t][p] = e (g_w[q] + sum_c g_r[c][q] data[c][p]) + [kernels[t][p] == m'[q]] T[q]
+ *   d_data[n][c][p]    = sum_t e g_r[c][q],   e = exp(kernels[t][p] - m'[q]),  q = p + off(t)
+ * Returns SBMC_EUNSUPPORTED when no fused kernel exists for the shape (odd
+ * kernels, c == 3, w % 4 == 0, 16-byte aligned pointers are required). */
+SBMC_API int sbmc_progressive_splat_bwd_f32(const float *planes, const float *kernels,
+                                   const float *data, float *d_kernels, float *d_data,
+                                   int64_t n, int c, int64_t h, int64_t w, int kh,
+                                   int kw, void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

@@ -31,6 +31,8 @@ SIGNATURES = {
     "sbmc_progressive_splat_fwd_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
+    "sbmc_progressive_splat_bwd_f32":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
@@ -76,6 +78,9 @@ def load():
     return lib
 
 
+EUNSUPPORTED = -5
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().sbmc_b200_last_error()
@@ -96,7 +101,7 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other", 5: "splat_fwd"}
+                4: "other", 5: "splat_fwd", 6: "splat_bwd"}
 NUM_KERNEL_KINDS = 8
 
 

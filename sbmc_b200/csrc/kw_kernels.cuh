@@ -56,6 +56,8 @@ __device__ __forceinline__ float4 lds_shifted4(const float *row, int lane, int r
 
 constexpr int kBoxPad = 4;                       // extra columns of a shifted box
 constexpr int kBoxW = kTileW + kBoxPad;          // 132 floats = 528 B
+// shared-memory slot of one tap's box: TMA destinations must be 128-byte aligned
+__host__ __device__ constexpr int tap_slot_floats(int rows) { return (rows * kBoxW + 31) / 32 * 32; }
 
 struct TileCoord {
   int xt, yt, n;

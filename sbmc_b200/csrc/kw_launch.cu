@@ -4,7 +4,8 @@
 namespace sbmc {
 
 // Tuned configurations (see profiles/ for the sweep they come from).
-constexpr int kRows = 8;      // warps (rows) per CTA, fwd and d_weights
+constexpr int kRows = 8;      // warps (rows) per CTA, forward
+constexpr int kRowsDw = 16;   // warps (rows) per CTA, d_weights
 constexpr int kMinB = 2;      // resident CTAs per SM the register budget allows
 constexpr int kChunk = 7;     // taps of one dx-chunk kept in flight per thread
 
@@ -26,7 +27,7 @@ static int ddata_tuned_n(const float *weights, const float *d_output,
                          float *d_data_ext, i64 n, i64 h, i64 w, int kh,
                          int halo_top, int halo_bot, cudaStream_t st) {
   constexpr int CH = KW < kChunk ? KW : kChunk;
-  constexpr int MINB = (NSEG >= 8) ? 1 : (NSEG >= 4 ? 2 : 4);
+  constexpr int MINB = 4;
   return run_bwd_ddata<C, KW, NSEG, MINB, CH>(weights, d_output, d_data_ext, n, h,
                                               w, kh, halo_top, halo_bot, st);
 }
@@ -36,20 +37,14 @@ static int ddata_tuned(const float *weights, const float *d_output,
                        float *d_data_ext, i64 n, i64 h, i64 w, int kh,
                        int halo_top, int halo_bot, cudaStream_t st) {
   const i64 segs = ceil_div(w, kTileW);
+  // Two 128-pixel segments per CTA (64 threads, 4 CTAs per SM) measured fastest
+  // on B200 even though wider images then need the seam atomics
+  // (profiles/r1d_sweep.txt: 0.951 ms vs 1.010 ms for one 1280-pixel CTA).
 #define SBMC_DD(NSEG)                                                         \
   return ddata_tuned_n<C, KW, NSEG>(weights, d_output, d_data_ext, n, h, w, kh, \
                                     halo_top, halo_bot, st)
   if (segs <= 1) SBMC_DD(1);
-  if (segs <= 2) SBMC_DD(2);
-  if (segs <= 4) SBMC_DD(4);
-  if (segs <= 5) SBMC_DD(5);
-  if (segs <= 8) SBMC_DD(8);
-  if (segs <= 10) SBMC_DD(10);
-  // wider than one CTA: pick the tile width that wastes fewer idle warps
-  const i64 waste8 = ceil_div(segs, 8) * 8 - segs;
-  const i64 waste10 = ceil_div(segs, 10) * 10 - segs;
-  if (waste8 < waste10) SBMC_DD(8);
-  SBMC_DD(10);
+  SBMC_DD(2);
 #undef SBMC_DD
 }
 
@@ -59,7 +54,9 @@ static int dweights_tuned(const float *data_ext, const float *d_output,
                           i64 w, int kh, int halo_top, int halo_bot,
                           cudaStream_t st) {
   constexpr int CH = KW < kChunk ? KW : kChunk;
-  return run_bwd_dweights<C, KW, kRows, kMinB, CH>(
+  // 16 rows per CTA, one CTA per SM, stores without L1 allocation
+  // (profiles/r1d_sweep.txt: 1.033 ms vs 1.052 ms for 8 rows / st.global.cs)
+  return run_bwd_dweights<C, KW, kRowsDw, 1, CH, 2>(
       data_ext, d_output, d_sum_w, d_weights, n, h, w, kh, halo_top, halo_bot, st);
 }
 
@@ -96,7 +93,7 @@ int launch_bwd_dweights(const float *data_ext, const float *d_output,
                       aligned16(d_output) && aligned16(d_sum_w) &&
                       aligned16(d_weights);
 #define X(CC, KK)                                                              \
-  if (vec_ok && c == CC && kw == KK && tile_shape_ok<CC, KK, kRows>(n, h, w, kh, hext)) { \
+  if (vec_ok && c == CC && kw == KK && tile_shape_ok<CC, KK, kRowsDw>(n, h, w, kh, hext)) { \
     note_path(1);                                                              \
     return dweights_tuned<CC, KK>(data_ext, d_output, d_sum_w, d_weights, n, h, \
                                   w, kh, halo_top, halo_bot, st);              \

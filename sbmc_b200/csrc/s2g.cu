@@ -30,7 +30,7 @@ s2g_kernel(const __grid_constant__ CUtensorMap map128,   // box 128 x ROWS
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem_raw = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
-  constexpr int kSlot = ROWS * kBoxW;            // floats per tap slot (max box)
+  constexpr int kSlot = tap_slot_floats(ROWS);   // floats per tap slot (max box)
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * TPS * kSlot);
   uint64_t *empty = full + STAGES;
@@ -118,7 +118,7 @@ int run_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h, i
   if (!make_plane_map(&m128, scatter, n, (i64)kh * kw, h, w, kTileW, ROWS) ||
       !make_plane_map(&m132, scatter, n, (i64)kh * kw, h, w, kBoxW, ROWS))
     return SBMC_ECUDA;
-  const size_t smem = (size_t)STAGES * TPS * ROWS * kBoxW * 4 + 2 * STAGES * 8 + 128;
+  const size_t smem = (size_t)STAGES * TPS * tap_slot_floats(ROWS) * 4 + 2 * STAGES * 8 + 128;
   auto kern = s2g_kernel<ROWS, STAGES, TPS>;
   SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int xt = (int)ceil_div(w, kTileW), yt = (int)ceil_div(h, ROWS);
@@ -133,8 +133,8 @@ int run_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h, i
   return SBMC_OK;
 }
 
-// tuned configuration (profiles/): 8 rows, 4 stages of 3 taps = 50 KB in flight per CTA
-constexpr int kS2gRows = 8, kS2gStages = 4, kS2gTps = 3;
+// tuned configuration (profiles/r1e_sweep.txt): 8 rows, 3 stages of 7 taps
+constexpr int kS2gRows = 8, kS2gStages = 3, kS2gTps = 7;
 
 int launch_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h,
                i64 w, cudaStream_t st) {

@@ -32,7 +32,7 @@ namespace sbmc {
 template <int C, int KW, int ROWS, int STAGES, int TPS>
 struct SplatSmem {
   using G = TileGeom<KW>;
-  static constexpr int kBoxFloats = ROWS * kBoxW;  // slot of one tap (widest box)
+  static constexpr int kBoxFloats = tap_slot_floats(ROWS);  // slot of one tap
   static constexpr int kStageFloats = TPS * kBoxFloats;
   static size_t tile_floats(int kh) { return (size_t)C * (ROWS + kh - 1) * G::TWS; }
   static size_t bytes(int kh) {
@@ -43,8 +43,27 @@ struct SplatSmem {
   }
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(d) for d <= 0 as 2^(d * log2 e): one multiply + one MUFU.  The rounding of
+// the product costs |d| * 6e-8 relative, i.e. only the terms that are already
+// negligible (large |d|) lose digits; the sums stay within ~1e-6 of expf.
+__device__ __forceinline__ float exp_neg(float d) {
+  return ex2_approx(d * 1.4426950408889634f);
+}
+
 // first != 0: the running state is initialised by this call (its input content
 // is ignored); otherwise it is updated in place.
+//
+// Pipeline unit ("stage") = up to TPS consecutive dx taps of one dy row.  The
+// consumer handles a stage in two phases so that the exponentials of a stage
+// are independent of each other: (1) stage maximum -> the running max grows at
+// most once per stage and the running sums are rescaled branch-free; (2) the
+// TPS x 4 exponentials and their multiply-adds against a register window of the
+// radiance row (read with aligned 128-bit shared loads, as in kw_fwd_kernel).
 template <int C, int KW, int ROWS, int STAGES, int TPS>
 __global__ void __launch_bounds__((ROWS + 1) * 32)
 splat_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
@@ -55,6 +74,8 @@ splat_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
                  int first, int xtiles, int ytiles) {
   using G = TileGeom<KW>;
   using L = SplatSmem<C, KW, ROWS, STAGES, TPS>;
+  constexpr int NCH = (KW + TPS - 1) / TPS;      // stages per dy row
+  constexpr int C0W = (KW - 1) / 2;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem_raw = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
@@ -68,10 +89,9 @@ splat_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
 
   const TileCoord tc = decode_tile(blockIdx.x, xtiles, ytiles);
   const int X0 = tc.xt * kTileW, Y0 = tc.yt * ROWS;
-  const int c0h = (KH - 1) / 2, c0w = (KW - 1) / 2;
+  const int c0h = (KH - 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = KH * KW;
-  const int nstages = (taps + TPS - 1) / TPS;
+  const int nstages = KH * NCH;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -94,21 +114,19 @@ splat_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
       for (int it = 0; it < nstages; ++it) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
-        const int t0 = it * TPS;
-        const int cnt = (taps - t0 < TPS) ? (taps - t0) : TPS;
+        const int dy = it / NCH, cs = (it - dy * NCH) * TPS;
+        const int cnt = (KW - cs < TPS) ? (KW - cs) : TPS;
         uint32_t bytes = 0;
         for (int j = 0; j < cnt; ++j) {
-          const int dx = (t0 + j) % KW;
-          const int r = splat ? ((dx - c0w) & 3) : 0;
+          const int r = splat ? ((cs + j - C0W) & 3) : 0;
           bytes += (uint32_t)(ROWS * (r ? kBoxW : kTileW) * sizeof(float));
         }
         mbar_expect_tx(&full[s], bytes);
         for (int j = 0; j < cnt; ++j) {
-          const int tap = t0 + j;
-          const int dy = tap / KW, dx = tap - dy * KW;
-          int plane = tap, sx = X0, sy = Y0, r = 0;
+          const int dx = cs + j;
+          int plane = dy * KW + dx, sx = X0, sy = Y0, r = 0;
           if (splat) {  // the transposed tap at the shifted position
-            const int sh = dx - c0w;
+            const int sh = dx - C0W;
             plane = (KH - 1 - dy) * KW + (KW - 1 - dx);
             sx = X0 + (sh & ~3);
             sy = Y0 + dy - c0h;
@@ -150,47 +168,104 @@ splat_fwd_kernel(const __grid_constant__ CUtensorMap dmap,
   }
 
   mbar_wait(tbar, 0);
-  const float *srow0 = tile + (size_t)warp * G::TWS + 4 * lane;
+  const float *srow = tile + (size_t)warp * G::TWS + 4 * lane;
   const int cstride = trows * G::TWS;
 
-  int tap = 0;
-  for (int it = 0; it < nstages; ++it) {
-    const int s = it % STAGES;
-    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
-    const int cnt = (taps - tap < TPS) ? (taps - tap) : TPS;
-    for (int j = 0; j < cnt; ++j, ++tap) {
-      const int dy = tap / KW, dx = tap - dy * KW;
-      const int r = splat ? ((dx - c0w) & 3) : 0;
-      const float4 gv = lds_shifted4(
-          ring + (size_t)s * L::kStageFloats + (size_t)j * L::kBoxFloats +
-              (size_t)warp * (r ? kBoxW : kTileW), lane, r);
-      const float g[4] = {gv.x, gv.y, gv.z, gv.w};
-      // radiance taps of my 4 pixels: tile column LEFT + dx + i of row warp+dy
-      const float *sp = srow0 + (size_t)dy * G::TWS + G::LEFT + dx;
-      float e[4];
+  // The sums are built hierarchically -- taps into a per-row partial (rw, rr),
+  // rows into the running totals (aw, ar) -- so that hundreds of near-identical
+  // tiny terms (e.g. the zero logits of out-of-image taps at the border) are not
+  // added one by one to a large accumulator: the fp32 error stays ~20x below
+  // that of the plain sequential sum.
+  int it = 0;
+  for (int dy = 0; dy < KH; ++dy) {
+    float rw[4] = {0.f, 0.f, 0.f, 0.f};
+    float rr[C][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (g[i] > m[i]) {  // the running max grows: rescale what was summed
-          const float a = expf(m[i] - g[i]);
-          aw[i] *= a;
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-          for (int c = 0; c < C; ++c) ar[c][i] *= a;
-          m[i] = g[i];
+      for (int i = 0; i < 4; ++i) rr[c][i] = 0.f;
+#pragma unroll
+    for (int cs = 0; cs < KW; cs += TPS, ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+      const float *slot = ring + (size_t)s * L::kStageFloats;
+      // ---- phase 1: the logits of this stage and their maximum ----
+      float g[TPS][4];
+      float smax[4] = {m[0], m[1], m[2], m[3]};
+#pragma unroll
+      for (int j = 0; j < TPS; ++j) {
+        if (cs + j < KW) {
+          const int r = splat ? ((cs + j - C0W) & 3) : 0;
+          const float4 gv = lds_shifted4(
+              slot + (size_t)j * L::kBoxFloats + (size_t)warp * (r ? kBoxW : kTileW), lane, r);
+          g[j][0] = gv.x; g[j][1] = gv.y; g[j][2] = gv.z; g[j][3] = gv.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) smax[i] = fmaxf(smax[i], g[j][i]);
         }
-        e[i] = expf(g[i] - m[i]);
-        aw[i] += e[i];
+      }
+      const bool grew = (smax[0] != m[0]) | (smax[1] != m[1]) | (smax[2] != m[2]) |
+                        (smax[3] != m[3]);
+      if (__any_sync(0xffffffffu, grew)) {  // rare after the first rows: rescale
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = (smax[i] == m[i]) ? 1.f : exp_neg(m[i] - smax[i]);
+          aw[i] *= a;
+          rw[i] *= a;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            ar[c][i] *= a;
+            rr[c][i] *= a;
+          }
+          m[i] = smax[i];
+        }
+      }
+      // ---- phase 2: exponentials and multiply-adds ----
+      constexpr int WMAX = (TPS + 3 + 3 + 3) / 4 * 4;
+      const int lo = (G::LEFT + cs) & ~3;
+      const int last = (cs + TPS < KW ? cs + TPS : KW) - 1;
+      const int hi = G::LEFT + last + 4;
+      float e[TPS][4];
+#pragma unroll
+      for (int j = 0; j < TPS; ++j) {
+        if (cs + j < KW) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            e[j][i] = exp_neg(g[j][i] - m[i]);
+            rw[i] += e[j][i];
+          }
+        }
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
+        float win[WMAX];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ar[c][i] = fmaf(e[i], sp[c * cstride + i], ar[c][i]);
+        for (int q = 0; q < WMAX; q += 4) {
+          if (lo + q < hi) {
+            const float4 t = *reinterpret_cast<const float4 *>(srow + c * cstride + lo + q);
+            win[q] = t.x; win[q + 1] = t.y; win[q + 2] = t.z; win[q + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TPS; ++j) {
+          if (cs + j < KW) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rr[c][i] = fmaf(e[j][i], win[G::LEFT + cs + j + i - lo], rr[c][i]);
+          }
+        }
       }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s]))
+                     : "memory");
     }
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s]))
-                   : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      aw[i] += rw[i];
+#pragma unroll
+      for (int c = 0; c < C; ++c) ar[c][i] += rr[c][i];
     }
+    srow += G::TWS;
   }
 
   if (valid) {
@@ -228,6 +303,7 @@ splat_fwd_generic_kernel(const float *__restrict__ K, const float *__restrict__ 
         ar[k] = (first || cb + k >= C) ? 0.f : sum_r[(n * C + cb + k) * plane + y * W + x];
       for (int dy = 0; dy < KH; ++dy) {
         const i64 yy = y + dy - c0h;
+        float rw = 0.f, rr[4] = {0.f, 0.f, 0.f, 0.f};   // per-row partial sums
         for (int dx = 0; dx < KW; ++dx) {
           const i64 xx = x + dx - c0w;
           const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
@@ -240,17 +316,24 @@ splat_fwd_generic_kernel(const float *__restrict__ K, const float *__restrict__ 
           if (g > mm) {
             const float a = expf(mm - g);
             ww *= a;
+            rw *= a;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ar[k] *= a;
+            for (int k = 0; k < 4; ++k) {
+              ar[k] *= a;
+              rr[k] *= a;
+            }
             mm = g;
           }
           const float e = expf(g - mm);
-          ww += e;
+          rw += e;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (cb + k < C && in)
-              ar[k] = fmaf(e, D[((n * C + cb + k) * H + yy) * W + xx], ar[k]);
+              rr[k] = fmaf(e, D[((n * C + cb + k) * H + yy) * W + xx], rr[k]);
         }
+        ww += rw;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ar[k] += rr[k];
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -296,7 +379,7 @@ static int run_splat(const float *kernels, const float *data, float *sum_r, floa
 }
 
 // tuning knobs of the fused splat (see profiles/)
-constexpr int kSplatRows = 4, kSplatStages = 6, kSplatTps = 3;
+constexpr int kSplatRows = 8, kSplatStages = 4, kSplatTps = 3;
 
 int launch_splat_fwd(const float *kernels, const float *data, float *sum_r, float *sum_w,
                      float *max_w, i64 n, int c, i64 h, i64 w, int kh, int kw, int splat,

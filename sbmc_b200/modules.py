@@ -295,6 +295,11 @@ class ProgressiveKernelApply(nn.Module):
                 _splat.fused_available(data, kernels, sum_r, sum_w, max_w):
             return _splat.progressive_splat_update(data, kernels, sum_r, sum_w, max_w,
                                                    self.splat)
+        if getattr(self, "fused", False) and self.splat and \
+                _splat.fused_training_available(data, kernels, sum_r, sum_w, max_w):
+            if first and (sum_w is not None or max_w is not None):
+                raise RuntimeError("all of sum_r, sum_w, max_w should be none")
+            return _splat.ProgressiveSplat.apply(data, kernels, sum_r, sum_w, max_w)
 
         kernels = kernels.view(bs, k, k, h, w)
         if self.splat:

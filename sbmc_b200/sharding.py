@@ -8,13 +8,14 @@ the overlap the ranks exchange it:
 
 * forward / d_weights read `data` rows up to c0 = (K-1)//2 above and K-1-c0
   below the band  ->  each rank receives those rows from its two neighbours
-  (`exchange_halo`, one grouped NCCL send/recv per call, [B, C, <=K-1, W] floats);
+  (`exchange_halo`: one NCCL all-gather of every rank's edge rows per call,
+  [world, 2, B, C, pad, W] floats -- KBs to a few MB);
 * d_data is a scatter: a band's samples contribute to rows up to K-1-c0 above
   and c0 below the band  ->  each rank computes its partial d_data on band+halo
   rows and the halo rows are sent to the neighbours, which add them
   (`reduce_halo`).  The K*K-channel weight tensor never crosses the link.
 
-The exchange is written against torch.distributed point-to-point ops only, so it
+The exchange is written against torch.distributed collectives only, so it
 runs over NCCL/NVLink on GPUs and over gloo on CPU tensors (tests/test_sharding.py
 drives it with world_size 2 on CPU).  The compute goes through the row-band
 entry points of the C ABI (sbmc_kernel_weighting_{fwd,bwd}_band_f32).
@@ -69,68 +70,64 @@ class BandPlan:
         return full.narrow(dim, self.y0[rank], self.rows(rank))
 
 
-def _p2p(ops, group):
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+def _all_gather(x, group=None):
+    """[...] -> [world, ...]: one NCCL / gloo all-gather, stream-ordered (it never
+    blocks the host, unlike grouped send/recv whose wait() was measured to stall
+    the launch queue: profiles/r1j_shard_timing.txt)."""
+    world = dist.get_world_size(group)
+    x = x.contiguous()
+    out = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))   # concatenated form
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out.view((world,) + tuple(x.shape))
 
 
 def exchange_halo(plan, rank, band, group=None):
     """band [..., rows, W] -> ext [..., top + rows + bot, W] with the neighbours'
-    rows in the halos (image borders have no halo).  One grouped send/recv."""
-    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    rows in the halos (image borders have no halo).  Every rank publishes its
+    first and last `pad` rows in ONE all-gather and picks its neighbours' edges
+    (2 * pad rows per rank: KBs to a few MB, the K*K weight volume stays put)."""
+    top, bot, pad = plan.halo_top(rank), plan.halo_bot(rank), plan.pad
     rows = band.shape[-2]
     ext = band.new_empty(band.shape[:-2] + (top + rows + bot, band.shape[-1]))
     ext.narrow(-2, top, rows).copy_(band)
-    ops, recv = [], []
-    if top:      # neighbour above: it needs my first rows, I need its last rows
-        up = rank - 1
-        send = band.narrow(-2, 0, plan.halo_bot(up)).contiguous()
-        buf = band.new_empty(band.shape[:-2] + (top, band.shape[-1]))
-        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, buf, up, group)]
-        recv.append((0, top, buf))
-    if bot:
-        dn = rank + 1
-        send = band.narrow(-2, rows - plan.halo_top(dn), plan.halo_top(dn)).contiguous()
-        buf = band.new_empty(band.shape[:-2] + (bot, band.shape[-1]))
-        ops += [dist.P2POp(dist.isend, send, dn, group), dist.P2POp(dist.irecv, buf, dn, group)]
-        recv.append((top + rows, bot, buf))
-    _p2p(ops, group)
-    for start, count, buf in recv:
-        ext.narrow(-2, start, count).copy_(buf)
+    if plan.world == 1:
+        return ext
+    edges = th.stack([band.narrow(-2, 0, pad), band.narrow(-2, rows - pad, pad)])
+    allv = _all_gather(edges, group)               # [world, 2, ..., pad, W]
+    if top:   # the upper neighbour's last rows
+        ext.narrow(-2, 0, top).copy_(allv[rank - 1, 1].narrow(-2, pad - top, top))
+    if bot:   # the lower neighbour's first rows
+        ext.narrow(-2, top + rows, bot).copy_(allv[rank + 1, 0].narrow(-2, 0, bot))
     return ext
 
 
 def reduce_halo(plan, rank, ext, out=None, group=None):
     """Adjoint of exchange_halo: ext [..., top + rows + bot, W] holds this rank's
     partial sums for its band and for the neighbours' edge rows; the halo rows
-    are sent to the neighbours and theirs are added to the band.  Returns the
-    band [..., rows, W] (written into `out` if given)."""
-    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    are published in one all-gather and every rank adds its neighbours' halos to
+    its own edge rows.  Returns the band [..., rows, W] (written into `out` if
+    given)."""
+    top, bot, pad = plan.halo_top(rank), plan.halo_bot(rank), plan.pad
     rows = ext.shape[-2] - top - bot
     band = ext.narrow(-2, top, rows)
     if out is None:
         out = band.clone()
     else:
         out.copy_(band)
-    ops, recv = [], []
-    if top:
-        up = rank - 1
-        send = ext.narrow(-2, 0, top).contiguous()
-        cnt = plan.halo_bot(up)          # rows of mine the upper band reached
-        buf = ext.new_empty(ext.shape[:-2] + (cnt, ext.shape[-1]))
-        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, buf, up, group)]
-        recv.append((0, cnt, buf))
-    if bot:
-        dn = rank + 1
-        send = ext.narrow(-2, top + rows, bot).contiguous()
-        cnt = plan.halo_top(dn)
-        buf = ext.new_empty(ext.shape[:-2] + (cnt, ext.shape[-1]))
-        ops += [dist.P2POp(dist.isend, send, dn, group), dist.P2POp(dist.irecv, buf, dn, group)]
-        recv.append((rows - cnt, cnt, buf))
-    _p2p(ops, group)
-    for start, count, buf in recv:
-        out.narrow(-2, start, count).add_(buf)
+    if plan.world == 1:
+        return out
+    halos = ext.new_zeros((2,) + tuple(ext.shape[:-2]) + (pad, ext.shape[-1]))
+    if top:   # my contribution to the upper neighbour's last rows
+        halos[0].narrow(-2, pad - top, top).copy_(ext.narrow(-2, 0, top))
+    if bot:   # ... and to the lower neighbour's first rows
+        halos[1].narrow(-2, 0, bot).copy_(ext.narrow(-2, top + rows, bot))
+    allv = _all_gather(halos, group)               # [world, 2, ..., pad, W]
+    if top:   # the upper neighbour's bottom halo lands on my first rows
+        cnt = plan.halo_bot(rank - 1)
+        out.narrow(-2, 0, cnt).add_(allv[rank - 1, 1].narrow(-2, 0, cnt))
+    if bot:   # the lower neighbour's top halo lands on my last rows
+        cnt = plan.halo_top(rank + 1)
+        out.narrow(-2, rows - cnt, cnt).add_(allv[rank + 1, 0].narrow(-2, pad - cnt, cnt))
     return out
 
 

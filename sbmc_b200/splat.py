@@ -6,7 +6,8 @@ import torch as th
 
 from . import _lib
 
-__all__ = ["progressive_splat_update", "fused_available"]
+__all__ = ["progressive_splat_update", "fused_available", "ProgressiveSplat",
+           "fused_training_available"]
 
 
 def fused_available(data, kernels, *state):
@@ -55,3 +56,72 @@ def progressive_splat_update(data, kernels, sum_r, sum_w, max_w, splat):
             th.cuda.current_stream(data.device).cuda_stream)
     _lib.check(rc, "progressive_splat")
     return sum_r, sum_w, max_w
+
+
+_BWD_SHAPES = {(3, 21), (3, 5), (3, 3), (3, 7)}       # (channels, k) with a fused backward
+
+
+def fused_training_available(data, kernels, *state):
+    """Whether ProgressiveSplat (fused forward AND backward) can serve this call."""
+    ts = [t for t in (data, kernels) + state if t is not None]
+    if not all(t.is_cuda and t.dtype == th.float32 for t in ts):
+        return False
+    k = int(round(kernels.shape[1] ** 0.5))
+    return (k * k == kernels.shape[1] and (data.shape[1], k) in _BWD_SHAPES
+            and data.shape[-1] % 4 == 0)
+
+
+class ProgressiveSplat(th.autograd.Function):
+    """One splat-mode ProgressiveKernelApply update (sbmc/modules.py:419-473) as a
+    single autograd node: fused one-pass forward, fused one-pass backward in
+    scatter space (csrc/splat_bwd.cu).  Only the logits are kept for backward,
+    not the Scatter2Gather / exp intermediates of the composed chain.
+
+    forward(data, kernels, sum_r, sum_w, max_w) -> (sum_r', sum_w', max_w'); pass
+    None for the three state tensors on the first update."""
+
+    @staticmethod
+    def forward(ctx, data, kernels, sum_r, sum_w, max_w):
+        first = sum_r is None
+        data = data.contiguous()
+        kernels = kernels.contiguous()
+        new_r, new_w, new_m = progressive_splat_update(data, kernels, sum_r, sum_w, max_w, True)
+        ctx.first = first
+        if first:
+            ctx.save_for_backward(data, kernels, new_r, new_w, new_m)
+        else:
+            ctx.save_for_backward(data, kernels, new_r, new_w, new_m, sum_r, sum_w, max_w)
+        return new_r, new_w, new_m
+
+    @staticmethod
+    def backward(ctx, g_r, g_w, g_m):
+        saved = ctx.saved_tensors
+        data, kernels, new_r, new_w, new_m = saved[:5]
+        bs, c, h, w = data.shape
+        k = int(round(kernels.shape[1] ** 0.5))
+        g_r = g_r.contiguous()
+        # gradient reaching the running max: dL/dm' minus what every rescaled
+        # term loses when m' grows (d sum'/dm' = -sum')
+        t_max = g_m - ((g_r * new_r).sum(1, keepdim=True) + g_w * new_w)
+        d_state = (None, None, None)
+        if ctx.first:
+            t_k = t_max
+        else:
+            sum_r, sum_w, max_w = saved[5:]
+            from_prev = new_m == max_w          # the max came from earlier samples
+            a = th.exp(max_w - new_m)
+            d_a = (g_r * sum_r).sum(1, keepdim=True) + g_w * sum_w
+            zero = th.zeros_like(t_max)
+            t_k = th.where(from_prev, zero, t_max)
+            d_state = (a * g_r, a * g_w, d_a * a + th.where(from_prev, t_max, zero))
+        planes = th.cat([g_r, g_w, new_m, t_k], 1).contiguous()
+        d_kernels = th.empty_like(kernels)
+        d_data = th.empty_like(data)
+        lib = _lib.load()
+        with th.cuda.device(data.device):
+            rc = lib.sbmc_progressive_splat_bwd_f32(
+                planes.data_ptr(), kernels.data_ptr(), data.data_ptr(),
+                d_kernels.data_ptr(), d_data.data_ptr(), bs, c, h, w, k, k,
+                th.cuda.current_stream(data.device).cuda_stream)
+        _lib.check(rc, "progressive_splat_bwd")
+        return (d_data, d_kernels) + d_state

@@ -255,6 +255,9 @@ def test_progressive_kernel_apply_gpu():
 
 @pytest.mark.gpu
 def test_multisteps_forward_gpu_matches_oracle_backed_cpu(monkeypatch):
+    # fp32 parity: keep cuDNN / cuBLAS off TF32 for this comparison
+    monkeypatch.setattr(th.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(th.backends.cuda.matmul, "allow_tf32", False)
     net, samples = _tiny_multisteps("cuda", train=True)
     out = net(samples)["radiance"]
     out.mean().backward()
@@ -301,10 +304,59 @@ def test_fused_progressive_matches_composed(shape, splat):
             assert _lib.launch_count() == before + 1          # one kernel per update
             b = composed(radiance[:, sp], logits[:, sp].clone(), *b)
             assert th.equal(a[2], b[2])                        # max_w: exact
-            assert th.allclose(a[1], b[1], rtol=1e-5, atol=0)
-            assert th.allclose(a[0], b[0], rtol=1e-5, atol=1e-6)
-    rr, rw, rm = (None, None, None)
+            # two fp32 evaluations of a K*K-term sum in different orders: at the
+            # image border the composed chain adds hundreds of identical tiny
+            # terms (zero logits of out-of-image taps) one by one, which costs it
+            # up to ~K*K*eps; the fused kernel sums hierarchically
+            assert th.allclose(a[1], b[1], rtol=1e-4, atol=0)
+            assert th.allclose(a[0], b[0], rtol=1e-4, atol=1e-5)
     if splat:
+        # against exact math (float64): the 1e-5 bar, for both paths
         rr, rw, rm = _softmax_splat_reference(radiance.cpu(), logits.cpu(), k)
-        assert th.allclose(a[1].cpu().double(), rw, rtol=1e-5)
-        assert th.allclose(a[0].cpu().double(), rr, rtol=1e-5, atol=1e-6)
+        for name, got in (("fused", a), ("composed", b)):
+            ew = ((got[1].cpu().double() - rw).abs() / rw).max().item()
+            er = ((got[0].cpu().double() - rr).abs() / (rr.abs() + rw)).max().item()
+            print("%s: max rel err sum_w %.2e sum_r %.2e" % (name, ew, er))
+            bar = 1e-5 if name == "fused" else 1e-4
+            assert ew <= bar and er <= bar, (name, ew, er)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 3, 24, 132, 5), (1, 3, 26, 256, 21), (1, 3, 12, 16, 3)])
+@pytest.mark.parametrize("loss_kind", ["normalized", "raw"])
+def test_fused_progressive_backward_matches_composed(shape, loss_kind):
+    """Gradients of a 3-sample progressive splat through the fused autograd node
+    against the reference chain of individual ops (both in fp32 on the GPU)."""
+    bs, c, h, w, k = shape
+    th.manual_seed(sum(shape))
+    spp = 3
+    radiance = th.rand(bs, spp, c, h, w, device="cuda")
+    logits = 3 * th.randn(bs, spp, k * k, h, w, device="cuda")
+    proj_r = th.randn(bs, c, h, w, device="cuda")
+    proj_w = th.randn(bs, 1, h, w, device="cuda")
+
+    def run(fused):
+        mod = modules.ProgressiveKernelApply(splat=True)
+        mod.fused = fused
+        r = radiance.clone().requires_grad_(True)
+        l = logits.clone().requires_grad_(True)
+        state = (None, None, None)
+        for sp in range(spp):
+            # (the composed chain modifies its kernels in place: hand it a copy)
+            state = mod(r[:, sp], l[:, sp] * 1.0, *state)
+        sum_r, sum_w, max_w = state
+        if loss_kind == "normalized":     # what Multisteps does (models.py:212)
+            loss = ((sum_r / (sum_w + 1e-8)) * proj_r).sum()
+        else:                              # the three outputs used independently
+            loss = (sum_r * proj_r).sum() + (sum_w * proj_w).sum() + (max_w * proj_w).sum()
+        loss.backward()
+        return loss.item(), r.grad, l.grad
+
+    la, ra, ka = run(True)
+    lb, rb, kb = run(False)
+    assert abs(la - lb) <= 1e-5 * abs(lb) + 1e-5
+    scale_r, scale_k = rb.abs().max().item(), kb.abs().max().item()
+    assert (ra - rb).abs().max().item() <= 1e-4 * scale_r, (ra - rb).abs().max().item() / scale_r
+    assert (ka - kb).abs().max().item() <= 1e-4 * scale_k, (ka - kb).abs().max().item() / scale_k
+    assert ((ka - kb).norm() / kb.norm()).item() <= 1e-5
+    assert ((ra - rb).norm() / rb.norm()).item() <= 1e-5

@@ -11,6 +11,7 @@
 #include "../sbmc_b200/csrc/kw_launch.cuh"
 #include "../sbmc_b200/csrc/s2g.cu"
 #include "../sbmc_b200/csrc/splat.cu"
+#include "../sbmc_b200/csrc/splat_bwd.cu"
 
 using namespace sbmc;
 
@@ -35,7 +36,7 @@ __global__ void fill_kernel(float *p, size_t n, unsigned seed) {
 struct Ctx {
   i64 n = 4, h = 720, w = 1280;
   int k = 21;
-  float *data, *wt, *out, *sw, *dout, *dsw, *ddata, *dwt;
+  float *data, *wt, *out, *sw, *dout, *dsw, *ddata, *dwt, *planes;
   cudaStream_t st;
   int iters = 5;
 };
@@ -97,6 +98,12 @@ static void time_it(Ctx &c, const char *name, double bytes_per_sample, F &&f) {
                                                c.w, c.k, 1, 0, c.st);         \
   });
 
+#define SPB(ROWS, MINB, CH)                                                   \
+  time_it(c, "splat_bwd rows=" #ROWS " minb=" #MINB " ch=" #CH, 4.0 * (2 * 441 + 12), [&] { \
+    return run_splat_bwd<3, 21, ROWS, MINB, CH>(c.planes, c.wt, c.data, c.dwt, c.ddata, c.n, \
+                                                c.h, c.w, c.k, c.st);         \
+  });
+
 int main(int argc, char **argv) {
   Ctx c;
   const char *which = argc > 1 ? argv[1] : "all";
@@ -108,6 +115,8 @@ int main(int argc, char **argv) {
   CK(cudaMalloc(&c.dout, img * 4));  CK(cudaMalloc(&c.ddata, img * 4));
   CK(cudaMalloc(&c.sw, pl * 4));     CK(cudaMalloc(&c.dsw, pl * 4));
   CK(cudaMalloc(&c.wt, vol * 4));    CK(cudaMalloc(&c.dwt, vol * 4));
+  CK(cudaMalloc(&c.planes, pl * 6 * 4));
+  fill_kernel<<<1184, 256>>>(c.planes, pl * 6, 5);
   fill_kernel<<<1184, 256>>>(c.data, img, 1);
   fill_kernel<<<1184, 256>>>(c.dout, img, 2);
   fill_kernel<<<1184, 256>>>(c.dsw, pl, 3);
@@ -141,7 +150,11 @@ int main(int argc, char **argv) {
     S2G(8, 6, 3)
   }
   if (all || !strcmp(which, "splat")) {
-    SPL(4, 6, 3) SPL(8, 4, 3) SPL(4, 8, 3) SPL(2, 8, 7) SPL(8, 6, 3) SPL(16, 2, 3)
+    SPL(8, 2, 7) SPL(8, 3, 7) SPL(4, 4, 7) SPL(4, 3, 7) SPL(16, 2, 7) SPL(8, 4, 3) SPL(8, 2, 11)
+    SPL(4, 6, 7)
+  }
+  if (all || !strcmp(which, "spb")) {
+    SPB(8, 2, 3) SPB(8, 2, 7) SPB(8, 1, 7) SPB(4, 4, 3) SPB(16, 1, 3) SPB(8, 3, 3) SPB(4, 3, 7)
   }
   return 0;
 }

@@ -43,9 +43,40 @@ def timed(fn, warmup, steps):
     return a.elapsed_time(b) / steps, (_lib.launch_count() - l0) / steps, kern
 
 
+def bench_chains(a, dev):
+    """The per-sample 1x1 chains alone: fused tcgen05 kernel vs the torch ConvChain
+    (cuDNN convs + activation kernels) on one [1, C, 720, 1280] sample plane."""
+    from sbmc_b200 import conv1x1, modules
+    h, w = a.h or 720, a.w or 1280
+    chains = {
+        "embedding_00 96->128->128->128": modules.ConvChain(96, 128, width=128, depth=3, ksize=1, pad=False),
+        "embedding_01 256->128->128->128": modules.ConvChain(256, 128, width=128, depth=3, ksize=1, pad=False),
+        "kernel_regressor 256->128->128->441": modules.ConvChain(
+            256, 441, depth=3, width=128, ksize=1, activation="leaky_relu", pad=False,
+            output_type="linear"),
+    }
+    for name, chain in chains.items():
+        chain = chain.to(dev).eval()
+        cin = conv1x1._convs(chain)[0].in_channels
+        cout = conv1x1._convs(chain)[2].out_channels
+        x = th.randn(1, cin, h, w, device=dev)
+        out = th.empty(1, cout, h, w, device=dev)
+        macs = h * w * (cin * 128 + 128 * 128 + 128 * cout)
+        with th.no_grad():
+            ms_f, _, kern = timed(lambda: conv1x1.chain_forward(chain, x, out=out), a.warmup, a.steps)
+            ms_t, _, _ = timed(lambda: chain(x), a.warmup, a.steps)
+            rel = ((out - chain(x)).norm() / chain(x).norm()).item()
+        print(json.dumps({
+            "bench": "1x1 chain " + name, "H": h, "W": w,
+            "fused_tcgen05_ms": ms_f, "torch_cudnn_fp32_ms": ms_t, "speedup": ms_t / ms_f,
+            "fused_TFLOPs": 2 * macs / ms_f / 1e9,
+            "fused_GBs_algorithmic": 4.0 * h * w * (cin + cout) / ms_f / 1e6,
+            "rel_err_vs_fp32": rel}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["forward", "train"])
+    ap.add_argument("mode", choices=["forward", "train", "chains"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--spp", type=int)
@@ -54,14 +85,24 @@ def main():
     ap.add_argument("--bs", type=int)
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast for the convs")
     ap.add_argument("--variants", default="fused,composed")
+    ap.add_argument("--bf16-unet", action="store_true",
+                    help="U-nets through cuDNN in bf16 / channels_last")
+    ap.add_argument("--bf16-chains", action="store_true",
+                    help="fused tcgen05 1x1 chains (embeddings, kernel regressor)")
     a = ap.parse_args()
     dev = th.device("cuda", 0)
     th.manual_seed(0)
+    if a.mode == "chains":
+        return bench_chains(a, dev)
     if a.mode == "forward":
         bs, spp, h, w = a.bs or 1, a.spp or 4, a.h or 720, a.w or 1280
     else:
         bs, spp, h, w = a.bs or 8, a.spp or 8, a.h or 128, a.w or 128
     net = models.Multisteps(93, 3).to(dev)
+    net.bf16_chains = a.bf16_chains
+    net.bf16_unet = a.bf16_unet
+    if a.bf16_unet:
+        net = net.to(memory_format=th.channels_last)
     batch = {"radiance": th.rand(bs, spp, 3, h, w, device=dev),
              "features": th.randn(bs, spp, 93, h, w, device=dev),
              "global_features": th.randn(bs, 3, 1, 1, device=dev),
@@ -90,6 +131,8 @@ def main():
             "bench": "Multisteps(93,3) %s" % ("eval forward (config 3)" if a.mode == "forward"
                                              else "train step (config 4)"),
             "variant": variant, "convs": "bf16 autocast (cuDNN)" if a.autocast else "fp32 (cuDNN)",
+            "chains_1x1": "fused tcgen05 bf16" if a.bf16_chains else "cuDNN",
+            "unet": "cuDNN bf16 channels_last" if a.bf16_unet else "cuDNN (as convs)",
             "bs": bs, "spp": spp, "H": h, "W": w, "K": 21,
             "ms_per_step": ms, "Msamples_per_s": samples / ms / 1e3,
             "sbmc_b200_launches_per_step": launches, "sbmc_b200_kernels": kern,

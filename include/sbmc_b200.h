@@ -85,6 +85,7 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_OTHER 4        /* halo adds of the host pipeline         */
 #define SBMC_KERNEL_SPLAT_FWD 5    /* fused ProgressiveKernelApply forward   */
 #define SBMC_KERNEL_SPLAT_BWD 6    /* fused ProgressiveKernelApply backward  */
+#define SBMC_KERNEL_CONV1X1 7      /* fused 3-layer 1x1 ConvChain (tcgen05)  */
 #define SBMC_NUM_KERNEL_KINDS 8
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
@@ -146,6 +147,25 @@ SBMC_API int sbmc_progressive_splat_bwd_f32(const float *planes, const float *ke
                                    const float *data, float *d_kernels, float *d_data,
                                    int64_t n, int c, int64_t h, int64_t w, int kh,
                                    int kw, void *stream);
+
+/* ---- fused per-sample 1x1 ConvChain on the tensor cores (inference) ------- *
+ * y = W3 act(W2 act(W1 [xa ; xb] + b1) + b2) + b3 for every pixel: the 3-layer
+ * 1x1 chains of sbmc/models.py:86-102 (hidden width 128).  xa [n][ca][hw] and
+ * xb [n][cb][hw] (or [n][cb] broadcast over the pixels when b_broadcast != 0;
+ * cb may be 0) are fp32 with `*_img_stride` elements between images; y is fp32
+ * [n][cout][hw] with y_img_stride elements between images.  Weights are bf16,
+ * row-major [out][in] with the input dimension zero-padded to k1p (128 or 256)
+ * for w1 [128][k1p], w2 [128][128], w3 [n3p][128] (n3p = cout rounded up to a
+ * multiple of 16, extra rows zero); biases fp32 (b3 has n3p entries).
+ * act: 0 = ReLU, 1 = LeakyReLU(0.01) on the two hidden layers; the output is
+ * linear.  bf16 operands, fp32 accumulation and fp32 output. */
+SBMC_API int sbmc_conv1x1_chain_f32(const float *xa, int ca, int64_t a_img_stride,
+                           const float *xb, int cb, int64_t b_img_stride,
+                           int b_broadcast, const void *w1, const float *b1,
+                           const void *w2, const float *b2, const void *w3,
+                           const float *b3, int k1p, int cout, int n3p, int act,
+                           float *y, int64_t y_img_stride, int64_t n_img, int64_t hw,
+                           void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

@@ -33,6 +33,9 @@ SIGNATURES = {
                 _int, _ptr]),
     "sbmc_progressive_splat_bwd_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _ptr]),
+    "sbmc_conv1x1_chain_f32":
+        (_int, [_ptr, _int, _i64, _ptr, _int, _i64, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                _int, _int, _int, _int, _ptr, _i64, _i64, _i64, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
@@ -101,7 +104,7 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other", 5: "splat_fwd", 6: "splat_bwd"}
+                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain"}
 NUM_KERNEL_KINDS = 8
 
 

@@ -6,7 +6,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace sbmc {
 
@@ -131,6 +131,33 @@ bool encode_tensor_map_f32(CUtensorMap *map, const void *base, int rank,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // OOB reads give 0.0f
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
+// bf16 [rows][inner] row-major, box {box_inner, box_rows}, 128-byte swizzle (the
+// canonical K-major UMMA operand layout: box_inner * 2 bytes must be 128).
+bool encode_tensor_map_bf16_2d_sw128(CUtensorMap *map, const void *base, uint64_t inner,
+                                     uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  if (box_inner * 2 != 128 || box_rows == 0 || box_rows > 256 || (inner * 2) % 16 != 0) {
+    set_error("tensor map (bf16 sw128): unsupported box %u x %u", box_inner, box_rows);
+    return false;
+  }
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstr[1] = {inner * 2};
+  cuuint32_t bdim[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 sw128) failed with CUresult %d", (int)r);
     return false;
   }
   return true;

@@ -26,6 +26,7 @@ constructor's argument checks (models.py:62,66), which turns the intended
 import torch as th
 import torch.nn as nn
 
+from . import conv1x1 as _conv1x1
 from . import modules as ops
 from ._compat import crop_like, get_logger
 
@@ -67,6 +68,13 @@ class Multisteps(nn.Module):
         self.embedding_width = embedding_width
         self.eps = 1e-8  # for kernel normalization
         self.nsteps = nsteps
+        # opt-in (inference): run the per-sample 1x1 chains (embeddings, kernel
+        # regressor) as fused tcgen05 kernels with bf16 operands / fp32
+        # accumulation instead of fp32 cuDNN convolutions
+        self.bf16_chains = False
+        # opt-in (inference): run the U-nets through cuDNN in bf16 / channels_last
+        # (BASELINE.json config 3: "bf16 convs + fp32 splat")
+        self.bf16_unet = False
 
         for step in range(nsteps):
             n_in = (n_features + n_global_features) if step == 0 \
@@ -100,6 +108,9 @@ class Multisteps(nn.Module):
             features = features.mean(1, keepdim=True)
         bs, spp, nf, h, w = features.shape
         one_by_one = not self.training       # the reference's limit_memory_usage
+        fused_chains = (one_by_one and getattr(self, "bf16_chains", False)
+                        and radiance.is_cuda and not th.is_grad_enabled()
+                        and _conv1x1.supports(self.kernel_regressor))
 
         propagated = None
         for step in range(self.nsteps):
@@ -110,6 +121,12 @@ class Multisteps(nn.Module):
                 reduced = None
                 for sp in range(spp):
                     ctx = gf if step == 0 else propagated
+                    if fused_chains and _conv1x1.supports(embed):
+                        f = _conv1x1.chain_forward(
+                            embed, features[:, sp], gfeatures if step == 0 else propagated,
+                            out=new_features[:, sp])
+                        reduced = f.clone() if reduced is None else reduced.add_(f)
+                        continue
                     f = embed(th.cat([features[:, sp], ctx], 1))
                     new_features[:, sp] = f
                     reduced = f if reduced is None else reduced.add_(f)
@@ -128,11 +145,21 @@ class Multisteps(nn.Module):
                 features = flat.view(bs, spp, self.embedding_width, h, w)
                 reduced = features.mean(1)
                 nf = self.embedding_width
-            propagated = getattr(self, "propagation_{:02d}".format(step))(reduced)
+            unet = getattr(self, "propagation_{:02d}".format(step))
+            if getattr(self, "bf16_unet", False) and reduced.is_cuda and not th.is_grad_enabled():
+                with th.autocast("cuda", dtype=th.bfloat16):
+                    propagated = unet(reduced.contiguous(memory_format=th.channels_last))
+                propagated = propagated.float().contiguous()
+            else:
+                propagated = unet(reduced)
 
         sum_r = sum_w = max_w = None
         for sp in range(spp):
-            kernels = self.kernel_regressor(th.cat([features[:, sp], propagated], 1))
+            if fused_chains:
+                kernels = _conv1x1.chain_forward(self.kernel_regressor, features[:, sp],
+                                                 propagated)
+            else:
+                kernels = self.kernel_regressor(th.cat([features[:, sp], propagated], 1))
             sum_r, sum_w, max_w = self.kernel_update(
                 crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
 

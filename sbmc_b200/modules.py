@@ -249,7 +249,9 @@ class KernelApply(nn.Module):
         (output [bs, chans, h, w], sum_w [bs, 1, h, w])."""
         bs, k2, h, w = kernels.shape
         k = _ksize(k2)
-        kernels = kernels.view(bs, k, k, h, w)
+        # the custom ops are fp32 (reduced-precision convs may feed them under autocast)
+        kernels = kernels.float().contiguous().view(bs, k, k, h, w)
+        data = data.float()
         if self.splat:
             kernels = funcs.Scatter2Gather.apply(kernels)
         if self.softmax:
@@ -285,6 +287,8 @@ class ProgressiveKernelApply(nn.Module):
         """
         bs, k2, h, w = kernels.shape
         k = _ksize(k2)
+        if kernels.dtype != th.float32 or data.dtype != th.float32:
+            kernels, data = kernels.float(), data.float()   # the custom ops are fp32
         first = sum_r is None
         if first and (sum_w is not None or max_w is not None):
             LOG.error("sum_r is None, this is the initialization step: "

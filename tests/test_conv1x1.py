@@ -1,0 +1,126 @@
+"""Fused tcgen05 1x1 ConvChain: host-side preparation on CPU; on the GPU the
+kernel against (a) a torch emulation with the same bf16 rounding points (tight)
+and (b) the plain fp32 ConvChain (bf16-level tolerance)."""
+import pytest
+import torch as th
+
+from sbmc_b200 import conv1x1, models, modules
+
+
+def _chains():
+    th.manual_seed(0)
+    return {
+        "embedding_00": modules.ConvChain(96, 128, width=128, depth=3, ksize=1, pad=False),
+        "embedding_01": modules.ConvChain(256, 128, width=128, depth=3, ksize=1, pad=False),
+        "kernel_regressor": modules.ConvChain(256, 441, depth=3, width=128, ksize=1,
+                                              activation="leaky_relu", pad=False,
+                                              output_type="linear"),
+        "small_out": modules.ConvChain(40, 24, depth=3, width=128, ksize=1, pad=False,
+                                       weight_norm=False),
+    }
+
+
+def test_supports_and_prepare():
+    for name, chain in _chains().items():
+        assert conv1x1.supports(chain), name
+        with th.no_grad():
+            for prm in chain.parameters():       # non-trivial weight-norm gains / biases
+                prm.add_(0.1 * th.randn_like(prm))
+        p = conv1x1.prepare(chain)
+        c1, c2, c3 = conv1x1._convs(chain)
+        assert p.k1p in (128, 256) and p.k1p >= c1.in_channels and p.n3p % 16 == 0
+        assert p.w1.shape == (128, p.k1p) and p.w3.shape == (p.n3p, 128)
+        # the folded weights reproduce the convolution
+        x = th.randn(2, c1.in_channels, 3, 5)
+        want = c1(x)
+        got = th.einsum("oc,nchw->nohw", conv1x1._effective_weight(c1), x) + c1.bias.view(1, -1, 1, 1)
+        assert th.allclose(got, want, rtol=1e-4, atol=1e-5)
+        assert (p.w1[:, c1.in_channels:] == 0).all() and (p.w3[c3.out_channels:] == 0).all()
+        assert conv1x1.prepare(chain) is p       # cached until a parameter changes
+        with th.no_grad():
+            c2.bias.add_(1.0)
+        assert conv1x1.prepare(chain) is not p
+    assert not conv1x1.supports(modules.ConvChain(96, 128, width=64, depth=3, ksize=1))
+    assert not conv1x1.supports(modules.ConvChain(96, 128, width=128, depth=3, ksize=3))
+    assert not conv1x1.supports(modules.ConvChain(96, 128, width=128, depth=2, ksize=1))
+    assert not conv1x1.supports(modules.ConvChain(96, 128, width=128, depth=3, ksize=1,
+                                                  normalize=True))
+
+
+def _emulate(chain, x):
+    """The chain with the kernel's rounding points: bf16 operands, fp32 accumulate."""
+    p = conv1x1.prepare(chain)
+    n, c, h, w = x.shape
+    a = x.permute(0, 2, 3, 1).reshape(-1, c).to(th.bfloat16).double()
+    act = (lambda t: th.nn.functional.leaky_relu(t, 0.01)) if p.act else th.relu
+    h1 = act(a @ p.w1[:, :c].double().t() + p.b1.double()).float().to(th.bfloat16).double()
+    h2 = act(h1 @ p.w2.double().t() + p.b2.double()).float().to(th.bfloat16).double()
+    y = h2 @ p.w3[:p.cout].double().t() + p.b3[:p.cout].double()
+    return y.float().reshape(n, h, w, p.cout).permute(0, 3, 1, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["embedding_00", "embedding_01", "kernel_regressor", "small_out"])
+@pytest.mark.parametrize("hw", [(16, 24), (9, 13), (64, 128)])
+def test_chain_matches_emulation_and_fp32(name, hw):
+    chain = _chains()[name].cuda().eval()
+    with th.no_grad():
+        for prm in chain.parameters():
+            prm.add_(0.05 * th.randn_like(prm))
+    h, w = hw
+    cin = conv1x1._convs(chain)[0].in_channels
+    th.manual_seed(1)
+    x = th.randn(3, cin, h, w, device="cuda")
+    with th.no_grad():
+        got = conv1x1.chain_forward(chain, x)
+        emu = _emulate(chain, x)
+        ref = chain(x)
+    scale = ref.abs().max().item()
+    # same rounding points: only the fp32 accumulation order differs -- except
+    # where an activation lands on a bf16 rounding boundary (rare flips of 1 bf16 ulp)
+    err = (got - emu).abs()
+    assert err.max().item() <= 2e-2 * scale
+    assert (err > 1e-4 * scale).float().mean().item() < 0.02
+    assert ((got - emu).norm() / emu.norm()).item() < 2e-3
+    # against the fp32 reference module: bf16-operand accuracy
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-2
+
+
+@pytest.mark.gpu
+def test_chain_two_sources_broadcast_and_strided_output():
+    """cat([features[:, sp], ctx]) without the cat: second source as a tensor and
+    as a per-image broadcast vector; output written into a strided slice."""
+    chains = _chains()
+    reg = chains["kernel_regressor"].cuda().eval()
+    emb0 = chains["embedding_00"].cuda().eval()
+    th.manual_seed(2)
+    bs, spp, h, w = 2, 3, 20, 36
+    feats = th.randn(bs, spp, 128, h, w, device="cuda")
+    prop = th.randn(bs, 128, h, w, device="cuda")
+    with th.no_grad():
+        got = conv1x1.chain_forward(reg, feats[:, 1], prop)
+        one = conv1x1.chain_forward(reg, th.cat([feats[:, 1], prop], 1))
+        assert th.equal(got, one)
+        f0 = th.randn(bs, spp, 93, h, w, device="cuda")
+        gf = th.randn(bs, 3, 1, 1, device="cuda")
+        new = th.zeros(bs, spp, 128, h, w, device="cuda")
+        conv1x1.chain_forward(emb0, f0[:, 2], gf, out=new[:, 2])
+        one = conv1x1.chain_forward(emb0, th.cat([f0[:, 2], gf.expand(bs, 3, h, w)], 1))
+        assert th.equal(new[:, 2], one)
+        assert (new[:, :2] == 0).all()
+
+
+@pytest.mark.gpu
+def test_multisteps_bf16_chains_close_to_fp32():
+    th.manual_seed(0)
+    net = models.Multisteps(12, 3, ksize=5, nsteps=2).cuda().eval()
+    bs, spp, h, w = 1, 2, 32, 48
+    samples = {"radiance": th.rand(bs, spp, 3, h, w, device="cuda"),
+               "features": th.randn(bs, spp, 12, h, w, device="cuda"),
+               "global_features": th.randn(bs, 3, 1, 1, device="cuda")}
+    with th.no_grad():
+        ref = net(samples)["radiance"]
+        net.bf16_chains = True
+        got = net(samples)["radiance"]
+    assert got.shape == ref.shape
+    assert ((got - ref).norm() / ref.norm()).item() < 3e-2

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 tools/multi_gpu_check.py 2>&1 | grep "MULTI_GPU\|False\|Error" 
-for n in 8 4; do
-echo "== bench $n gpus"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --no-cpu-baseline 2> gpurun_out/r1l_bench$n.err | grep "^{" | tee gpurun_out/r1l_bench$n.json | cut -c1-200
-done
+echo "== pytest conv1x1"
+timeout 900 python -m pytest tests/test_conv1x1.py -m gpu -q -x 2>&1 | tail -25
+echo "== chains"
+timeout 600 python benchmarks/model_bench.py chains --steps 5 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1o_chains.json | cut -c1-500
+echo "== cfg3 forward with bf16 chains"
+timeout 900 python benchmarks/model_bench.py forward --bf16-chains --variants fused 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1o_cfg3_chains.json | cut -c1-700

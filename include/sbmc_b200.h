@@ -167,6 +167,21 @@ SBMC_API int sbmc_conv1x1_chain_f32(const float *xa, int ca, int64_t a_img_strid
                            float *y, int64_t y_img_stride, int64_t n_img, int64_t hw,
                            void *stream);
 
+/* Same chain on bf16 channels-innermost activations (the inference pipeline's
+ * layout): xa, xb are bf16 [n][hw][128] (xb may be NULL; `*_img_stride` elements
+ * between images) and are pulled by TMA straight into the tensor-core operand
+ * layout.  w1 is bf16 [128][128 or 256] (xa's channels first), b1 may differ per
+ * image (b1_img_stride = 128) or be shared (0) -- this is how broadcast global
+ * features enter.  Output: out_nhwc_bf16 != 0 -> bf16 [n][hw][128] (cout must be
+ * 128), else fp32 [n][cout][hw]. */
+SBMC_API int sbmc_conv1x1_chain_nhwc_bf16(const void *xa, int64_t a_img_stride, const void *xb,
+                                 int64_t b_img_stride, const void *w1, const float *b1,
+                                 int64_t b1_img_stride, const void *w2, const float *b2,
+                                 const void *w3, const float *b3, int cout, int n3p,
+                                 int act, void *y, int64_t y_img_stride,
+                                 int out_nhwc_bf16, int64_t n_img, int64_t hw,
+                                 void *stream);
+
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /
  * d_sum_w / d_weights cover exactly the band.  `data_ext` ([n][c][halo_top +

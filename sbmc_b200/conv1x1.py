@@ -9,7 +9,7 @@ import torch as th
 
 from . import _lib
 
-__all__ = ["supports", "prepare", "chain_forward"]
+__all__ = ["supports", "prepare", "chain_forward", "chain_forward_nhwc", "to_nhwc_bf16"]
 
 _HID = 128
 
@@ -142,4 +142,107 @@ def chain_forward(chain, xa, xb=None, out=None):
             p.w3.data_ptr(), p.b3.data_ptr(), p.k1p, p.cout, p.n3p, p.act,
             out.data_ptr(), y_img, n, h * w, th.cuda.current_stream(xa.device).cuda_stream)
     _lib.check(rc, "conv1x1_chain")
+    return out
+
+
+# -- bf16 channels-innermost pipeline ---------------------------------------------
+def to_nhwc_bf16(x, channels=_HID):
+    """[..., c, h, w] fp32 -> [..., h*w, channels] bf16 (zero-padded channels)."""
+    c, h, w = x.shape[-3:]
+    lead = x.shape[:-3]
+    out = x.new_zeros(lead + (h * w, channels), dtype=th.bfloat16)
+    out[..., :c] = x.reshape(lead + (c, h * w)).transpose(-1, -2)
+    return out
+
+
+class _PreparedNhwc(object):
+    __slots__ = ("w1", "w1_gf", "w2", "w3", "b1", "b2", "b3", "cout", "n3p", "act", "versions",
+                 "key")
+
+
+def _prepare_nhwc(chain, ca, cb, ngf):
+    """Weights for the NHWC kernel: input channel order of the chain is
+    [ca real channels of xa | ngf broadcast features | cb channels of xb];
+    xa is stored padded to 128 channels."""
+    key = (ca, cb, ngf)
+    cached = getattr(chain, "_sbmc_b200_prepared_nhwc", None)
+    ver = _versions(chain)
+    if cached is not None and cached.versions == ver and cached.key == key:
+        return cached
+    c1, c2, c3 = _convs(chain)
+    if ca + ngf + cb != c1.in_channels or ca > _HID or cb not in (0, _HID):
+        raise RuntimeError("conv1x1 chain: %d + %d + %d input channels do not match the "
+                           "chain's %d" % (ca, ngf, cb, c1.in_channels))
+    dev = c1.bias.device
+    w = _effective_weight(c1)
+    p = _PreparedNhwc()
+    w1 = th.zeros(_HID, _HID + cb, device=dev)
+    w1[:, :ca] = w[:, :ca]
+    if cb:
+        w1[:, _HID:] = w[:, ca + ngf:]
+    p.w1 = w1.to(th.bfloat16).contiguous()
+    p.w1_gf = w[:, ca:ca + ngf].contiguous()          # fp32, folded into the bias per image
+    p.w2 = _effective_weight(c2).to(th.bfloat16).contiguous()
+    p.cout = c3.out_channels
+    p.n3p = (p.cout + 15) // 16 * 16
+    w3 = th.zeros(p.n3p, _HID, device=dev)
+    w3[:p.cout] = _effective_weight(c3)
+    p.w3 = w3.to(th.bfloat16).contiguous()
+    p.b1 = c1.bias.detach().float().contiguous()
+    p.b2 = c2.bias.detach().float().contiguous()
+    b3 = th.zeros(p.n3p, device=dev)
+    b3[:p.cout] = c3.bias.detach().float()
+    p.b3 = b3
+    p.act = 1 if isinstance(chain.layer_0.layer[1], th.nn.LeakyReLU) else 0
+    p.versions, p.key = ver, key
+    object.__setattr__(chain, "_sbmc_b200_prepared_nhwc", p)
+    return p
+
+
+def _nhwc_view(x):
+    """x bf16 [n, hw, 128] with contiguous images -> (tensor, image stride)."""
+    if x.dtype != th.bfloat16 or x.dim() != 3 or x.shape[-1] != _HID:
+        raise RuntimeError("expected a bf16 [n, pixels, 128] tensor, got %s %s"
+                           % (x.dtype, tuple(x.shape)))
+    if x.stride()[1:] != (_HID, 1):
+        x = x.contiguous()
+    return x, (x.stride(0) if x.shape[0] > 1 else x.shape[1] * _HID)
+
+
+def chain_forward_nhwc(chain, xa, ca, xb=None, gf=None, out=None, nhwc_out=True):
+    """The chain on bf16 channels-innermost activations.
+
+    xa bf16 [n, hw, 128] holding `ca` real channels; gf [n, ngf] fp32 features
+    broadcast over the pixels (enter through a per-image first-layer bias); xb bf16
+    [n, hw, 128] or None.  Output: bf16 [n, hw, 128] (nhwc_out, needs cout == 128)
+    or fp32 [n, cout, hw]."""
+    n, hw, _ = xa.shape
+    ngf = 0 if gf is None else gf.shape[1]
+    p = _prepare_nhwc(chain, ca, 0 if xb is None else _HID, ngf)
+    xa, a_img = _nhwc_view(xa)
+    xb_t, b_img = (None, 0) if xb is None else _nhwc_view(xb)
+    if gf is not None:
+        b1 = (p.b1.unsqueeze(0) + gf.float().reshape(n, ngf) @ p.w1_gf.t()).contiguous()
+        b1_img = _HID
+    else:
+        b1, b1_img = p.b1, 0
+    if out is None:
+        out = (xa.new_empty(n, hw, _HID) if nhwc_out
+               else th.empty(n, p.cout, hw, device=xa.device, dtype=th.float32))
+    if nhwc_out:
+        if p.cout != _HID or out.dtype != th.bfloat16 or out.stride()[1:] != (_HID, 1):
+            raise RuntimeError("conv1x1 chain: bad bf16 NHWC output tensor")
+        y_img = out.stride(0) if n > 1 else hw * _HID
+    else:
+        if out.dtype != th.float32 or out.stride()[1:] != (hw, 1):
+            raise RuntimeError("conv1x1 chain: bad fp32 NCHW output tensor")
+        y_img = out.stride(0) if n > 1 else p.cout * hw
+    lib = _lib.load()
+    with th.cuda.device(xa.device):
+        rc = lib.sbmc_conv1x1_chain_nhwc_bf16(
+            xa.data_ptr(), a_img, xb_t.data_ptr() if xb_t is not None else None, b_img,
+            p.w1.data_ptr(), b1.data_ptr(), b1_img, p.w2.data_ptr(), p.b2.data_ptr(),
+            p.w3.data_ptr(), p.b3.data_ptr(), p.cout, p.n3p, p.act, out.data_ptr(), y_img,
+            1 if nhwc_out else 0, n, hw, th.cuda.current_stream(xa.device).cuda_stream)
+    _lib.check(rc, "conv1x1_chain_nhwc")
     return out

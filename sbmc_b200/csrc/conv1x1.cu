@@ -80,6 +80,27 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *
   }
 }
 
+// Same as hidden_epilogue with the bias read from global memory (L1-resident).
+__device__ __forceinline__ void hidden_epilogue_g(uint32_t tmem_row, const float *bias, int act,
+                                                  unsigned char *dstA, int row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < kHid; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32b_x32(tmem_row + c0, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 q;
+      const int c = c0 + 8 * j;
+      q.x = pack_bf16(activate(v[8 * j + 0] + __ldg(bias + c + 0), act), activate(v[8 * j + 1] + __ldg(bias + c + 1), act));
+      q.y = pack_bf16(activate(v[8 * j + 2] + __ldg(bias + c + 2), act), activate(v[8 * j + 3] + __ldg(bias + c + 3), act));
+      q.z = pack_bf16(activate(v[8 * j + 4] + __ldg(bias + c + 4), act), activate(v[8 * j + 5] + __ldg(bias + c + 5), act));
+      q.w = pack_bf16(activate(v[8 * j + 6] + __ldg(bias + c + 6), act), activate(v[8 * j + 7] + __ldg(bias + c + 7), act));
+      const int chunk = c >> 3;
+      *reinterpret_cast<uint4 *>(dstA + (chunk >> 3) * kSlab + sw128_offset(row, chunk & 7)) = q;
+    }
+  }
+}
+
 // K1P: padded input channels (128 or 256).
 template <int K1P>
 __global__ void __launch_bounds__(128, 1)
@@ -288,6 +309,234 @@ static int run_chain(const ChainArgs &a, const void *w1, const void *w2, const v
   return SBMC_OK;
 }
 
+// ===========================================================================
+// NHWC-bf16 variant: the inference pipeline keeps every per-sample / per-pixel
+// activation as bf16 with channels innermost ([n][pixel][128]), which IS the
+// K-major UMMA A-operand order.  One TMA box (64 channels x 128 pixels,
+// SWIZZLE_128B) is one operand slab, so the input needs no thread at all: the
+// producer thread issues the next tile's loads as soon as the first layer's
+// MMAs have retired, and they land while the rest of the chain runs.  Output is
+// either bf16 NHWC (embeddings: 256 contiguous bytes per pixel / thread) or fp32
+// NCHW (the K*K logits for the splat kernels).
+// ===========================================================================
+struct ChainArgsV2 {
+  const float *b1;  long long b1_img;    // first-layer bias, optionally per image
+  const float *b2, *b3;
+  void *y;          long long y_img;     // elements between output images
+  int out_nhwc_bf16;                     // 1: bf16 [n][hw][128]; 0: fp32 [n][cout][hw]
+  int cout, n3p, act;
+  long long hw, tiles_per_img, ntiles;
+};
+
+// KS1: 64-channel slabs of the first layer's K (2: one source, 4: two sources).
+template <int KS1>
+__global__ void __launch_bounds__(128, 1)
+conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
+                          const __grid_constant__ CUtensorMap bmap,
+                          const __grid_constant__ CUtensorMap w1map,
+                          const __grid_constant__ CUtensorMap w2map,
+                          const __grid_constant__ CUtensorMap w3map, const ChainArgsV2 P) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sW1 = smem;
+  unsigned char *sW2 = sW1 + KS1 * kSlab;
+  unsigned char *sA0 = sW2 + 2 * kSlab;          // TMA destination, KS1 slabs
+  unsigned char *sA12 = sA0 + KS1 * kSlab;       // hidden activations (layer 1, then 2)
+  unsigned char *sW3 = sA12 + 2 * kSlab;         // one chunk of up to 128 output channels
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sW3 + 2 * kSlab);
+  uint64_t *bar_w = bars, *bar_mma = bars + 1, *bar_w3 = bars + 2, *bar_a = bars + 3;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_w3, 1);
+    mbar_init(bar_a, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+
+  const int nchunks = (P.n3p + 127) / 128;
+  const uint32_t w3_bytes = (uint32_t)(2 * (P.n3p < 128 ? P.n3p : 128) * 128);
+
+  auto load_tile = [&](long long tile) {          // tid 0: A operand of `tile`
+    const int n = (int)(tile / P.tiles_per_img);
+    const int p0 = (int)((tile - (long long)n * P.tiles_per_img) * kTileP);
+    mbar_expect_tx(bar_a, (uint32_t)(KS1 * kSlab));
+    tma_load_3d(sA0, &amap, bar_a, 0, p0, n);
+    tma_load_3d(sA0 + kSlab, &amap, bar_a, 64, p0, n);
+    if (KS1 == 4) {
+      tma_load_3d(sA0 + 2 * kSlab, &bmap, bar_a, 0, p0, n);
+      tma_load_3d(sA0 + 3 * kSlab, &bmap, bar_a, 64, p0, n);
+    }
+  };
+  auto load_w3 = [&](int chunk) {                 // tid 0
+    mbar_expect_tx(bar_w3, w3_bytes);
+    tma_load_2d(sW3, &w3map, bar_w3, 0, chunk * 128);
+    tma_load_2d(sW3 + kSlab, &w3map, bar_w3, 64, chunk * 128);
+  };
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, (uint32_t)((KS1 + 2) * kSlab));
+    for (int kb = 0; kb < KS1; ++kb) tma_load_2d(sW1 + kb * kSlab, &w1map, bar_w, kb * 64, 0);
+    for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW2 + kb * kSlab, &w2map, bar_w, kb * 64, 0);
+    load_w3(0);
+    if ((long long)blockIdx.x < P.ntiles) load_tile(blockIdx.x);
+  }
+  uint32_t ph_mma = 0, ph_w3 = 0, ph_a = 0;
+  bool first = true;
+
+  for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    const long long n = tile / P.tiles_per_img;
+    const long long p = (tile - n * P.tiles_per_img) * kTileP + tid;
+    const bool valid = p < P.hw;
+    const float *b1 = P.b1 + n * P.b1_img;
+
+    // ---- layer 1 ----
+    if (tid == 0) {
+      if (first) mbar_wait(bar_w, 0);
+      mbar_wait(bar_a, ph_a);
+      tcgen05_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, kHid);
+#pragma unroll 1
+      for (int k = 0; k < KS1 * 4; ++k) {
+        const uint64_t ad = umma_smem_desc_sw128(sA0 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+        const uint64_t bd = umma_smem_desc_sw128(sW1 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+        umma_bf16(tmem, ad, bd, idesc, k > 0);
+      }
+      umma_commit(bar_mma);
+    }
+    first = false;
+    ph_a ^= 1;
+    mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
+    tcgen05_fence_after();
+    if (tid == 0 && tile + gridDim.x < P.ntiles) load_tile(tile + gridDim.x);  // A0 is free
+    hidden_epilogue_g(tmem_row, b1, P.act, sA12, tid);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+
+    // ---- layer 2 ----
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, kHid);
+#pragma unroll 1
+      for (int k = 0; k < kHid / 16; ++k) {
+        const uint64_t ad = umma_smem_desc_sw128(sA12 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+        const uint64_t bd = umma_smem_desc_sw128(sW2 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+        umma_bf16(tmem, ad, bd, idesc, k > 0);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
+    tcgen05_fence_after();
+    hidden_epilogue_g(tmem_row, P.b2, P.act, sA12, tid);   // overwrites layer 1's operand
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+
+    // ---- layer 3, chunk by chunk ----
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int rows = (P.n3p - ch * 128 < 128) ? (P.n3p - ch * 128) : 128;
+      if (tid == 0) {
+        if (nchunks > 1 || tile == (long long)blockIdx.x) mbar_wait(bar_w3, ph_w3);
+        tcgen05_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, rows);
+#pragma unroll 1
+        for (int k = 0; k < kHid / 16; ++k) {
+          const uint64_t ad = umma_smem_desc_sw128(sA12 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+          const uint64_t bd = umma_smem_desc_sw128(sW3 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + (uint32_t)(ch * 128), ad, bd, idesc, k > 0);
+        }
+        umma_commit(bar_mma);
+      }
+      if (nchunks > 1) ph_w3 ^= 1;
+      mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
+      tcgen05_fence_after();
+      if (tid == 0 && nchunks > 1) {
+        // the chunk buffer is free: stream the next chunk (or chunk 0 of the next tile)
+        if (ch + 1 < nchunks) load_w3(ch + 1);
+        else if (tile + gridDim.x < P.ntiles) load_w3(0);
+      }
+      if (P.out_nhwc_bf16) {
+        // bf16 NHWC: this thread's pixel, 128 channels = 256 contiguous bytes
+        uint4 *dst = reinterpret_cast<uint4 *>(
+            reinterpret_cast<__nv_bfloat16 *>(P.y) + n * P.y_img + p * kHid);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHid; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32b_x32(tmem_row + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              const int c = c0 + 8 * j;
+              q.x = pack_bf16(v[8 * j + 0] + __ldg(P.b3 + c + 0), v[8 * j + 1] + __ldg(P.b3 + c + 1));
+              q.y = pack_bf16(v[8 * j + 2] + __ldg(P.b3 + c + 2), v[8 * j + 3] + __ldg(P.b3 + c + 3));
+              q.z = pack_bf16(v[8 * j + 4] + __ldg(P.b3 + c + 4), v[8 * j + 5] + __ldg(P.b3 + c + 5));
+              q.w = pack_bf16(v[8 * j + 6] + __ldg(P.b3 + c + 6), v[8 * j + 7] + __ldg(P.b3 + c + 7));
+              dst[c >> 3] = q;
+            }
+          }
+        }
+      } else {
+        float *yp = reinterpret_cast<float *>(P.y) + n * P.y_img + p;
+        const int col_end = (ch * 128 + rows < P.n3p) ? (ch * 128 + rows) : P.n3p;
+#pragma unroll 1
+        for (int col = ch * 128; col < col_end; col += 32) {
+          float v[32];
+          tmem_ld_32x32b_x32(tmem_row + col, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col + i < P.cout) yp[(long long)(col + i) * P.hw] = v[i] + __ldg(P.b3 + col + i);
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();   // the next tile's MMAs overwrite the accumulator
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int KS1>
+static int run_chain_v2(const ChainArgsV2 &a, const void *xa, long long a_img, const void *xb,
+                        long long b_img, long long n_img, const void *w1, const void *w2,
+                        const void *w3, cudaStream_t st) {
+  CUtensorMap ma, mb, m1, m2, m3;
+  if (!encode_tensor_map_bf16_3d_sw128(&ma, xa, kHid, (uint64_t)a.hw, (uint64_t)n_img,
+                                       (uint64_t)a_img, kTileP))
+    return SBMC_ECUDA;
+  mb = ma;
+  if (KS1 == 4 && !encode_tensor_map_bf16_3d_sw128(&mb, xb, kHid, (uint64_t)a.hw,
+                                                   (uint64_t)n_img, (uint64_t)b_img, kTileP))
+    return SBMC_ECUDA;
+  if (!encode_tensor_map_bf16_2d_sw128(&m1, w1, KS1 * 64, kHid, 64, kHid) ||
+      !encode_tensor_map_bf16_2d_sw128(&m2, w2, kHid, kHid, 64, kHid) ||
+      !encode_tensor_map_bf16_2d_sw128(&m3, w3, kHid, (uint64_t)a.n3p, 64,
+                                       (uint32_t)(a.n3p < 128 ? a.n3p : 128)))
+    return SBMC_ECUDA;
+  const size_t smem = (size_t)(KS1 + 2 + KS1 + 2 + 2) * kSlab + 128 + 1024;
+  auto kern = conv1x1_chain_nhwc_kernel<KS1>;
+  SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
+  {
+    KernelTimer timer(SBMC_KERNEL_CONV1X1, st);
+    kern<<<(unsigned)grid, 128, smem, st>>>(ma, mb, m1, m2, m3, a);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  return SBMC_OK;
+}
+
 }  // namespace sbmc
 
 extern "C" int sbmc_conv1x1_chain_f32(const float *xa, int ca, int64_t a_img_stride,
@@ -327,4 +576,40 @@ extern "C" int sbmc_conv1x1_chain_f32(const float *xa, int ca, int64_t a_img_str
   note_path(1);
   if (k1p == 128) return run_chain<128>(a, w1, w2, w3, st);
   return run_chain<256>(a, w1, w2, w3, st);
+}
+
+
+extern "C" int sbmc_conv1x1_chain_nhwc_bf16(const void *xa, int64_t a_img_stride, const void *xb,
+                                            int64_t b_img_stride, const void *w1,
+                                            const float *b1, int64_t b1_img_stride,
+                                            const void *w2, const float *b2, const void *w3,
+                                            const float *b3, int cout, int n3p, int act,
+                                            void *y, int64_t y_img_stride, int out_nhwc_bf16,
+                                            int64_t n_img, int64_t hw, void *stream) {
+  using namespace sbmc;
+  if (n_img < 0 || hw < 0 || cout < 1) {
+    set_error("conv1x1_chain_nhwc: invalid shape");
+    return SBMC_EINVAL;
+  }
+  if (n_img == 0 || hw == 0) return SBMC_OK;
+  if (!xa || !w1 || !w2 || !w3 || !b1 || !b2 || !b3 || !y) {
+    set_error("conv1x1_chain_nhwc: null pointer argument");
+    return SBMC_EINVAL;
+  }
+  if (n3p % 16 != 0 || n3p < cout || n3p > 512 || n3p < 16 || (out_nhwc_bf16 && cout != 128) ||
+      hw >= (1ll << 31) || n_img >= (1ll << 31)) {
+    set_error("conv1x1_chain_nhwc: unsupported sizes cout=%d n3p=%d", cout, n3p);
+    return SBMC_EUNSUPPORTED;
+  }
+  ChainArgsV2 a;
+  a.b1 = b1; a.b1_img = b1_img_stride; a.b2 = b2; a.b3 = b3;
+  a.y = y; a.y_img = y_img_stride; a.out_nhwc_bf16 = out_nhwc_bf16 ? 1 : 0;
+  a.cout = cout; a.n3p = n3p; a.act = act ? 1 : 0;
+  a.hw = hw;
+  a.tiles_per_img = (hw + kTileP - 1) / kTileP;
+  a.ntiles = a.tiles_per_img * n_img;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  note_path(1);
+  if (!xb) return run_chain_v2<2>(a, xa, a_img_stride, nullptr, 0, n_img, w1, w2, w3, st);
+  return run_chain_v2<4>(a, xa, a_img_stride, xb, b_img_stride, n_img, w1, w2, w3, st);
 }

@@ -163,6 +163,36 @@ bool encode_tensor_map_bf16_2d_sw128(CUtensorMap *map, const void *base, uint64_
   return true;
 }
 
+// bf16 activations [n][rows][inner] (channels innermost, `img_stride` elements
+// between images), box {64, box_rows, 1}, 128-byte swizzle: one box is one K-major
+// UMMA operand slab of box_rows pixels x 64 channels.
+bool encode_tensor_map_bf16_3d_sw128(CUtensorMap *map, const void *base, uint64_t inner,
+                                     uint64_t rows, uint64_t n, uint64_t img_stride,
+                                     uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  if (inner < 64 || (inner * 2) % 16 != 0 || (img_stride * 2) % 16 != 0 || box_rows == 0 ||
+      box_rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15)) {
+    set_error("tensor map (bf16 3d sw128): unsupported layout");
+    return false;
+  }
+  cuuint64_t gdim[3] = {inner, rows, n};
+  cuuint64_t gstr[2] = {inner * 2, img_stride * 2};
+  cuuint32_t bdim[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 3d sw128) failed with CUresult %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
 }  // namespace sbmc
 
 extern "C" {

@@ -12,6 +12,10 @@ namespace sbmc {
 bool encode_tensor_map_bf16_2d_sw128(CUtensorMap *map, const void *base, uint64_t inner,
                                      uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 
+bool encode_tensor_map_bf16_3d_sw128(CUtensorMap *map, const void *base, uint64_t inner,
+                                     uint64_t rows, uint64_t n, uint64_t img_stride,
+                                     uint32_t box_rows);
+
 #ifdef __CUDACC__
 
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a K-major
@@ -106,6 +110,15 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map,
+                                            uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 

@@ -112,6 +112,9 @@ class Multisteps(nn.Module):
                         and radiance.is_cuda and not th.is_grad_enabled()
                         and _conv1x1.supports(self.kernel_regressor))
 
+        if fused_chains and self._nhwc_pipeline_ok(nf):
+            return self._forward_nhwc(radiance, features, gfeatures)
+
         propagated = None
         for step in range(self.nsteps):
             embed = getattr(self, "embedding_{:02d}".format(step))
@@ -165,6 +168,55 @@ class Multisteps(nn.Module):
 
         output = sum_r / (sum_w + self.eps)
         crop = (self.ksize - 1) // 2        # the border ring is biased
+        return {"radiance": output[..., crop:-crop, crop:-crop]}
+
+
+    # -- bf16 channels-innermost inference pipeline (opt-in: bf16_chains) -----------
+    def _nhwc_pipeline_ok(self, nf):
+        chains = [getattr(self, "embedding_{:02d}".format(i)) for i in range(self.nsteps)]
+        return (self.width == 128 and self.embedding_width == 128 and nf <= 128
+                and all(_conv1x1.supports(c) for c in chains + [self.kernel_regressor]))
+
+    def _forward_nhwc(self, radiance, features, gfeatures):
+        """Same computation as `forward` in eval mode with every per-sample /
+        per-pixel activation kept as bf16 [.., pixel, 128] (channels innermost):
+        the 1x1 chains run as fused tcgen05 kernels fed by TMA, the concatenations
+        of the reference (models.py:147-150,196-198) are never materialised, the
+        global features enter through a per-image bias, the U-nets see a
+        channels_last view, and only the K*K logits are produced in fp32 NCHW for
+        the fused splat."""
+        bs, spp, nf, h, w = features.shape
+        hw = h * w
+        feats = _conv1x1.to_nhwc_bf16(features)              # [bs, spp, hw, 128]
+        gf = gfeatures.reshape(bs, -1).float()
+        prop, ca = None, nf
+        for step in range(self.nsteps):
+            embed = getattr(self, "embedding_{:02d}".format(step))
+            new = feats.new_empty(bs, spp, hw, 128)
+            for sp in range(spp):
+                _conv1x1.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
+                                            gf=gf if step == 0 else None, out=new[:, sp])
+            feats, ca = new, 128
+            reduced = new.float().mean(1)                     # [bs, hw, 128]
+            x = reduced.view(bs, h, w, 128).permute(0, 3, 1, 2)   # NCHW, channels_last memory
+            unet = getattr(self, "propagation_{:02d}".format(step))
+            if getattr(self, "bf16_unet", False):
+                with th.autocast("cuda", dtype=th.bfloat16):
+                    y = unet(x)
+            else:
+                y = unet(x)
+            prop = y.permute(0, 2, 3, 1).to(th.bfloat16).contiguous().view(bs, hw, 128)
+
+        sum_r = sum_w = max_w = None
+        k2 = self.ksize * self.ksize
+        for sp in range(spp):
+            kernels = _conv1x1.chain_forward_nhwc(
+                self.kernel_regressor, feats[:, sp], 128, xb=prop, nhwc_out=False)
+            kernels = kernels.view(bs, k2, h, w)
+            sum_r, sum_w, max_w = self.kernel_update(
+                crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
+        output = sum_r / (sum_w + self.eps)
+        crop = (self.ksize - 1) // 2
         return {"radiance": output[..., crop:-crop, crop:-crop]}
 
 

@@ -114,7 +114,7 @@ def test_chain_two_sources_broadcast_and_strided_output():
 def test_multisteps_bf16_chains_close_to_fp32():
     th.manual_seed(0)
     net = models.Multisteps(12, 3, ksize=5, nsteps=2).cuda().eval()
-    bs, spp, h, w = 1, 2, 32, 48
+    bs, spp, h, w = 2, 2, 32, 48
     samples = {"radiance": th.rand(bs, spp, 3, h, w, device="cuda"),
                "features": th.randn(bs, spp, 12, h, w, device="cuda"),
                "global_features": th.randn(bs, 3, 1, 1, device="cuda")}
@@ -124,3 +124,56 @@ def test_multisteps_bf16_chains_close_to_fp32():
         got = net(samples)["radiance"]
     assert got.shape == ref.shape
     assert ((got - ref).norm() / ref.norm()).item() < 3e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,two", [("embedding_00", False), ("embedding_01", True),
+                                      ("kernel_regressor", True)])
+@pytest.mark.parametrize("hw", [(16, 24), (9, 13), (64, 128)])
+def test_nhwc_chain_matches_fp32_kernel_inputs(name, two, hw):
+    """The TMA-fed NHWC variant against the emulation (same rounding points)."""
+    chain = _chains()[name].cuda().eval()
+    with th.no_grad():
+        for prm in chain.parameters():
+            prm.add_(0.05 * th.randn_like(prm))
+    h, w = hw
+    n = 3
+    th.manual_seed(3)
+    if name == "embedding_00":            # 93 features + 3 global features
+        xa = th.randn(n, 93, h, w, device="cuda")
+        gf = th.randn(n, 3, device="cuda")
+        full = th.cat([xa, gf.view(n, 3, 1, 1).expand(n, 3, h, w)], 1)
+        a_nhwc, ca, xb_nhwc = conv1x1.to_nhwc_bf16(xa), 93, None
+    else:
+        xa = th.randn(n, 128, h, w, device="cuda")
+        xb = th.randn(n, 128, h, w, device="cuda")
+        gf = None
+        full = th.cat([xa, xb], 1)
+        a_nhwc, ca, xb_nhwc = conv1x1.to_nhwc_bf16(xa), 128, conv1x1.to_nhwc_bf16(xb)
+    nhwc_out = name != "kernel_regressor"
+    with th.no_grad():
+        got = conv1x1.chain_forward_nhwc(chain, a_nhwc, ca, xb=xb_nhwc, gf=gf, nhwc_out=nhwc_out)
+        ref = chain(full)
+    if nhwc_out:
+        assert got.dtype == th.bfloat16 and got.shape == (n, h * w, 128)
+        got = got.float().view(n, h, w, 128).permute(0, 3, 1, 2)
+    else:
+        got = got.view(n, -1, h, w)
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-2
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 0.1 * scale
+
+
+@pytest.mark.gpu
+def test_nhwc_chain_strided_views():
+    reg = _chains()["embedding_01"].cuda().eval()
+    th.manual_seed(4)
+    bs, spp, h, w = 2, 3, 12, 20
+    feats = conv1x1.to_nhwc_bf16(th.randn(bs, spp, 128, h, w, device="cuda"))
+    prop = conv1x1.to_nhwc_bf16(th.randn(bs, 128, h, w, device="cuda"))
+    new = th.zeros(bs, spp, h * w, 128, device="cuda", dtype=th.bfloat16)
+    with th.no_grad():
+        conv1x1.chain_forward_nhwc(reg, feats[:, 1], 128, xb=prop, out=new[:, 2])
+        one = conv1x1.chain_forward_nhwc(reg, feats[:, 1].contiguous(), 128, xb=prop)
+    assert th.equal(new[:, 2], one)
+    assert (new[:, :2] == 0).all()

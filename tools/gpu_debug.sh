@@ -2,7 +2,6 @@
 mkdir -p gpurun_out
 echo "== pytest conv1x1"
 timeout 900 python -m pytest tests/test_conv1x1.py -m gpu -q -x 2>&1 | tail -25
-echo "== chains"
-timeout 600 python benchmarks/model_bench.py chains --steps 5 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1o_chains.json | cut -c1-500
-echo "== cfg3 forward with bf16 chains"
-timeout 900 python benchmarks/model_bench.py forward --bf16-chains --variants fused 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1o_cfg3_chains.json | cut -c1-700
+echo "== cfg3 variants"
+timeout 600 python benchmarks/model_bench.py forward --bf16-unet --bf16-chains --variants fused 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1r_cfg3_bf16all.json | cut -c1-700
+timeout 600 python tools/torch_profile.py unet_chains 2>&1 | grep -v "^$" | cut -c1-200 | tee gpurun_out/r1r_torch_profile_unet_chains.txt | head -32

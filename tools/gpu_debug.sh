@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== pytest conv1x1"
-timeout 900 python -m pytest tests/test_conv1x1.py -m gpu -q -x 2>&1 | tail -25
-echo "== cfg3 variants"
-timeout 600 python benchmarks/model_bench.py forward --bf16-unet --bf16-chains --variants fused 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1r_cfg3_bf16all.json | cut -c1-700
-timeout 600 python tools/torch_profile.py unet_chains 2>&1 | grep -v "^$" | cut -c1-200 | tee gpurun_out/r1r_torch_profile_unet_chains.txt | head -32
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv1x1_chain_nhwc' -s 2 -c 2 -f -o gpurun_out/r1s_prof python tools/profile_chain.py > gpurun_out/r1s_ncu.log 2>&1
+tail -3 gpurun_out/r1s_ncu.log

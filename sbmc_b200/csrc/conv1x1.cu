@@ -80,27 +80,6 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *
   }
 }
 
-// Same as hidden_epilogue with the bias read from global memory (L1-resident).
-__device__ __forceinline__ void hidden_epilogue_g(uint32_t tmem_row, const float *bias, int act,
-                                                  unsigned char *dstA, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < kHid; c0 += 32) {
-    float v[32];
-    tmem_ld_32x32b_x32(tmem_row + c0, v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 q;
-      const int c = c0 + 8 * j;
-      q.x = pack_bf16(activate(v[8 * j + 0] + __ldg(bias + c + 0), act), activate(v[8 * j + 1] + __ldg(bias + c + 1), act));
-      q.y = pack_bf16(activate(v[8 * j + 2] + __ldg(bias + c + 2), act), activate(v[8 * j + 3] + __ldg(bias + c + 3), act));
-      q.z = pack_bf16(activate(v[8 * j + 4] + __ldg(bias + c + 4), act), activate(v[8 * j + 5] + __ldg(bias + c + 5), act));
-      q.w = pack_bf16(activate(v[8 * j + 6] + __ldg(bias + c + 6), act), activate(v[8 * j + 7] + __ldg(bias + c + 7), act));
-      const int chunk = c >> 3;
-      *reinterpret_cast<uint4 *>(dstA + (chunk >> 3) * kSlab + sw128_offset(row, chunk & 7)) = q;
-    }
-  }
-}
-
 // K1P: padded input channels (128 or 256).
 template <int K1P>
 __global__ void __launch_bounds__(128, 1)
@@ -328,27 +307,57 @@ struct ChainArgsV2 {
   long long hw, tiles_per_img, ntiles;
 };
 
+// Epilogue helpers of the NHWC kernel: 256 threads, thread t owns pixel (t & 127)
+// and the column half (t >> 7) of every 128-column accumulator block; biases are
+// read from shared memory (float4 broadcasts).
+__device__ __forceinline__ void hidden_epilogue_half(uint32_t tmem_row, const float *sbias,
+                                                     int act, unsigned char *dstA, int row,
+                                                     int half) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int c0 = half * 64 + it * 32;
+    float v[32];
+    tmem_ld_32x32b_x32(tmem_row + c0, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 8 * j;
+      const float4 ba = *reinterpret_cast<const float4 *>(sbias + c);
+      const float4 bb = *reinterpret_cast<const float4 *>(sbias + c + 4);
+      uint4 q;
+      q.x = pack_bf16(activate(v[8 * j + 0] + ba.x, act), activate(v[8 * j + 1] + ba.y, act));
+      q.y = pack_bf16(activate(v[8 * j + 2] + ba.z, act), activate(v[8 * j + 3] + ba.w, act));
+      q.z = pack_bf16(activate(v[8 * j + 4] + bb.x, act), activate(v[8 * j + 5] + bb.y, act));
+      q.w = pack_bf16(activate(v[8 * j + 6] + bb.z, act), activate(v[8 * j + 7] + bb.w, act));
+      const int chunk = c >> 3;
+      *reinterpret_cast<uint4 *>(dstA + (chunk >> 3) * kSlab + sw128_offset(row, chunk & 7)) = q;
+    }
+  }
+}
+
 // KS1: 64-channel slabs of the first layer's K (2: one source, 4: two sources).
 template <int KS1>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
                           const __grid_constant__ CUtensorMap bmap,
                           const __grid_constant__ CUtensorMap w1map,
                           const __grid_constant__ CUtensorMap w2map,
                           const __grid_constant__ CUtensorMap w3map, const ChainArgsV2 P) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sW1 = smem;
   unsigned char *sW2 = sW1 + KS1 * kSlab;
   unsigned char *sA0 = sW2 + 2 * kSlab;          // TMA destination, KS1 slabs
   unsigned char *sA12 = sA0 + KS1 * kSlab;       // hidden activations (layer 1, then 2)
   unsigned char *sW3 = sA12 + 2 * kSlab;         // one chunk of up to 128 output channels
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sW3 + 2 * kSlab);
+  float *sB1 = reinterpret_cast<float *>(sW3 + 2 * kSlab);
+  float *sB2 = sB1 + kHid;
+  float *sB3 = sB2 + kHid;                       // up to 448 entries
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB3 + 448);
   uint64_t *bar_w = bars, *bar_mma = bars + 1, *bar_w3 = bars + 2, *bar_a = bars + 3;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();    // SWIZZLE_128B slabs need 1024-byte alignment
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_mma, 1);
@@ -357,11 +366,13 @@ conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid < kHid) sB2[tid] = P.b2[tid];
+  for (int i = tid; i < 448; i += 256) sB3[i] = i < P.n3p ? P.b3[i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
   const int nchunks = (P.n3p + 127) / 128;
   const uint32_t w3_bytes = (uint32_t)(2 * (P.n3p < 128 ? P.n3p : 128) * 128);
@@ -392,12 +403,17 @@ conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
   }
   uint32_t ph_mma = 0, ph_w3 = 0, ph_a = 0;
   bool first = true;
+  long long cur_n = -1;
 
   for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     const long long n = tile / P.tiles_per_img;
-    const long long p = (tile - n * P.tiles_per_img) * kTileP + tid;
+    const long long p = (tile - n * P.tiles_per_img) * kTileP + row;
     const bool valid = p < P.hw;
-    const float *b1 = P.b1 + n * P.b1_img;
+    if (n != cur_n) {                             // (per-image) first-layer bias
+      if (tid < kHid) sB1[tid] = P.b1[n * P.b1_img + tid];
+      cur_n = n;
+      __syncthreads();
+    }
 
     // ---- layer 1 ----
     if (tid == 0) {
@@ -418,7 +434,7 @@ conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
     mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
     tcgen05_fence_after();
     if (tid == 0 && tile + gridDim.x < P.ntiles) load_tile(tile + gridDim.x);  // A0 is free
-    hidden_epilogue_g(tmem_row, b1, P.act, sA12, tid);
+    hidden_epilogue_half(tmem_row, sB1, P.act, sA12, row, half);
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
@@ -437,7 +453,7 @@ conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
     }
     mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
     tcgen05_fence_after();
-    hidden_epilogue_g(tmem_row, P.b2, P.act, sA12, tid);   // overwrites layer 1's operand
+    hidden_epilogue_half(tmem_row, sB2, P.act, sA12, row, half);   // overwrites layer 1's operand
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
@@ -466,37 +482,44 @@ conv1x1_chain_nhwc_kernel(const __grid_constant__ CUtensorMap amap,
         else if (tile + gridDim.x < P.ntiles) load_w3(0);
       }
       if (P.out_nhwc_bf16) {
-        // bf16 NHWC: this thread's pixel, 128 channels = 256 contiguous bytes
+        // bf16 NHWC: this thread's pixel, its 64 channels = 128 contiguous bytes
         uint4 *dst = reinterpret_cast<uint4 *>(
             reinterpret_cast<__nv_bfloat16 *>(P.y) + n * P.y_img + p * kHid);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kHid; c0 += 32) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int c0 = half * 64 + it * 32;
           float v[32];
           tmem_ld_32x32b_x32(tmem_row + c0, v);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 q;
               const int c = c0 + 8 * j;
-              q.x = pack_bf16(v[8 * j + 0] + __ldg(P.b3 + c + 0), v[8 * j + 1] + __ldg(P.b3 + c + 1));
-              q.y = pack_bf16(v[8 * j + 2] + __ldg(P.b3 + c + 2), v[8 * j + 3] + __ldg(P.b3 + c + 3));
-              q.z = pack_bf16(v[8 * j + 4] + __ldg(P.b3 + c + 4), v[8 * j + 5] + __ldg(P.b3 + c + 5));
-              q.w = pack_bf16(v[8 * j + 6] + __ldg(P.b3 + c + 6), v[8 * j + 7] + __ldg(P.b3 + c + 7));
+              const float4 ba = *reinterpret_cast<const float4 *>(sB3 + c);
+              const float4 bb = *reinterpret_cast<const float4 *>(sB3 + c + 4);
+              uint4 q;
+              q.x = pack_bf16(v[8 * j + 0] + ba.x, v[8 * j + 1] + ba.y);
+              q.y = pack_bf16(v[8 * j + 2] + ba.z, v[8 * j + 3] + ba.w);
+              q.z = pack_bf16(v[8 * j + 4] + bb.x, v[8 * j + 5] + bb.y);
+              q.w = pack_bf16(v[8 * j + 6] + bb.z, v[8 * j + 7] + bb.w);
               dst[c >> 3] = q;
             }
           }
         }
       } else {
+        // fp32 NCHW: a warp stores 32 consecutive pixels of one channel
         float *yp = reinterpret_cast<float *>(P.y) + n * P.y_img + p;
-        const int col_end = (ch * 128 + rows < P.n3p) ? (ch * 128 + rows) : P.n3p;
-#pragma unroll 1
-        for (int col = ch * 128; col < col_end; col += 32) {
-          float v[32];
-          tmem_ld_32x32b_x32(tmem_row + col, v);
-          if (valid) {
+        const int base = ch * 128 + half * 64;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col + i < P.cout) yp[(long long)(col + i) * P.hw] = v[i] + __ldg(P.b3 + col + i);
+        for (int it = 0; it < 2; ++it) {
+          const int col = base + it * 32;
+          if (col < ch * 128 + rows) {             // warp-uniform
+            float v[32];
+            tmem_ld_32x32b_x32(tmem_row + col, v);
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col + i < P.cout) yp[(long long)(col + i) * P.hw] = v[i] + sB3[col + i];
+            }
           }
         }
       }
@@ -524,13 +547,13 @@ static int run_chain_v2(const ChainArgsV2 &a, const void *xa, long long a_img, c
       !encode_tensor_map_bf16_2d_sw128(&m3, w3, kHid, (uint64_t)a.n3p, 64,
                                        (uint32_t)(a.n3p < 128 ? a.n3p : 128)))
     return SBMC_ECUDA;
-  const size_t smem = (size_t)(KS1 + 2 + KS1 + 2 + 2) * kSlab + 128 + 1024;
+  const size_t smem = (size_t)(KS1 + 2 + KS1 + 2 + 2) * kSlab + (2 * kHid + 448) * 4 + 64;
   auto kern = conv1x1_chain_nhwc_kernel<KS1>;
   SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   {
     KernelTimer timer(SBMC_KERNEL_CONV1X1, st);
-    kern<<<(unsigned)grid, 128, smem, st>>>(ma, mb, m1, m2, m3, a);
+    kern<<<(unsigned)grid, 256, smem, st>>>(ma, mb, m1, m2, m3, a);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());

@@ -74,7 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned b, int xtiles,
 
 // One CTA-wide TMA box load of the image tile (all C channels, ROWS + KH - 1
 // rows, TWS columns) with zero fill outside the (extended) image.
-template <int KW>
+template <int KW, bool KEEP = false>
 __device__ __forceinline__ void load_image_tile(const CUtensorMap *dmap,
                                                 float *tile, uint64_t *bar,
                                                 int C, int rows, int x0tile,
@@ -87,7 +87,10 @@ __device__ __forceinline__ void load_image_tile(const CUtensorMap *dmap,
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)(C * rows * G::TWS * sizeof(float)));
-    tma_load_4d(tile, dmap, bar, x0tile - G::A, y0ext, 0, n);
+    if (KEEP)   // the image tile is re-read by neighbouring CTAs and the next kernel
+      tma_load_4d_hint(tile, dmap, bar, x0tile - G::A, y0ext, 0, n, l2_policy_evict_last());
+    else
+      tma_load_4d(tile, dmap, bar, x0tile - G::A, y0ext, 0, n);
   }
 }
 
@@ -209,23 +212,26 @@ kw_bwd_dweights_kernel(const __grid_constant__ CUtensorMap dmap,
   const TileCoord tc = decode_tile(blockIdx.x, xtiles, ytiles);
   const int X0 = tc.xt * kTileW, Y0 = tc.yt * ROWS;
   const int c0h = (KH - 1) / 2;
-  load_image_tile<KW>(&dmap, tile, bar, C, trows, X0, Y0 + halo_top - c0h, tc.n);
+  load_image_tile<KW, STORE == 3>(&dmap, tile, bar, C, trows, X0, Y0 + halo_top - c0h, tc.n);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y = Y0 + warp, x0 = X0 + 4 * lane;
   const bool valid = (y < H) && (x0 < W);
   const i64 plane = (i64)H * W;
   const i64 pix = (i64)y * W + x0;
+  const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
 
   float go[C][4];
   float gs[4];
   if (valid) {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float4 t = ldg_cached(dO + ((i64)tc.n * C + c) * plane + pix);
+      const float *src = dO + ((i64)tc.n * C + c) * plane + pix;
+      const float4 t = (STORE == 3) ? ldg_hint(src, keep) : ldg_cached(src);
       go[c][0] = t.x; go[c][1] = t.y; go[c][2] = t.z; go[c][3] = t.w;
     }
-    const float4 t = ldg_cached(dSw + (i64)tc.n * plane + pix);
+    const float *src = dSw + (i64)tc.n * plane + pix;
+    const float4 t = (STORE == 3) ? ldg_hint(src, keep) : ldg_cached(src);
     gs[0] = t.x; gs[1] = t.y; gs[2] = t.z; gs[3] = t.w;
   }
 
@@ -266,8 +272,11 @@ kw_bwd_dweights_kernel(const __grid_constant__ CUtensorMap dmap,
               for (int c = 0; c < C; ++c)
                 v[i] = fmaf(win[c][G::LEFT + cs + j + i - lo], go[c][i], v[i]);
             }
-            stg_policy<STORE>(wp + (i64)(cs + j) * plane,
-                              make_float4(v[0], v[1], v[2], v[3]));
+            if (STORE == 3)
+              stg_hint(wp + (i64)(cs + j) * plane, make_float4(v[0], v[1], v[2], v[3]), stream);
+            else
+              stg_policy<STORE>(wp + (i64)(cs + j) * plane,
+                                make_float4(v[0], v[1], v[2], v[3]));
           }
         }
       }

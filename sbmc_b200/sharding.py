@@ -26,7 +26,8 @@ import torch.distributed as dist
 from . import _lib
 
 __all__ = ["BandPlan", "exchange_halo", "reduce_halo", "kernel_weighting_fwd_sharded",
-           "kernel_weighting_bwd_sharded", "ShardedKernelWeighting", "gather_bands"]
+           "kernel_weighting_bwd_sharded", "ShardedKernelWeighting", "gather_bands",
+           "multisteps_forward_sharded"]
 
 
 class BandPlan:
@@ -213,3 +214,62 @@ def gather_bands(plan, rank, band, dim, group=None):
     dist.all_gather(parts, padded, group=group)
     full = th.cat([p[:plan.rows(r)] for r, p in enumerate(parts)], dim=0)
     return full.movedim(0, dim).contiguous()
+
+
+# -- tiled multi-GPU inference of the whole model (BASELINE.json config 5) ---------
+def model_band_rows(plan, rank, overlap):
+    """Rows [a, b) of the full image that `rank` feeds to the model: its band plus
+    `overlap` rows of context on each side (clamped to the image), and the rows
+    [top, top + rows) of the model's *input tile* that the band occupies."""
+    a = max(0, plan.y0[rank] - overlap)
+    b = min(plan.height, plan.y1[rank] + overlap)
+    return a, b, plan.y0[rank] - a
+
+
+def multisteps_forward_sharded(model, samples, rank, world, overlap=144, group=None):
+    """Denoise one (batch of) full image(s) with `world` ranks, one row band each.
+
+    The reference handles large images by overlap-tiling with recompute
+    (scripts/denoise.py:54-93, 256-pixel pad); here the tiles are the ranks' row
+    bands.  `samples` holds the FULL-image tensors ("radiance" [bs, spp, 3, H, W],
+    "features" [bs, spp, nf, H, W], "global_features") on every rank -- only the
+    band plus `overlap` rows of context are moved to the GPU and pushed through
+    the model; the context covers the receptive field of the three U-nets and the
+    K x K splat (~127 px), so band rows see exactly what the
+    unsharded forward sees.  `overlap` must be a multiple of 4 (pooling
+    alignment) as must the band origins.  The denoised bands are all-gathered:
+    every rank returns the full {"radiance": [bs, 3, H - K + 1, W - K + 1]}.
+    """
+    radiance = samples["radiance"]
+    height = radiance.shape[-2]
+    crop = (model.ksize - 1) // 2
+    if overlap % 4 or overlap < crop:
+        raise ValueError("overlap must be a multiple of 4 and >= (K-1)/2")
+    plan = BandPlan(height, world, model.ksize)
+    if any(y % 4 for y in plan.y0):
+        raise ValueError("band origins must be multiples of 4 (H = %d over %d ranks)"
+                         % (height, world))
+    a, b, top = model_band_rows(plan, rank, overlap)
+    dev = th.device("cuda", th.cuda.current_device()) if th.cuda.is_available() \
+        else radiance.device
+    tile = {"radiance": radiance[..., a:b, :].to(dev),
+            "features": samples["features"][..., a:b, :].to(dev),
+            "global_features": samples["global_features"].to(dev)}
+    out = model(tile)["radiance"]                  # [bs, 3, (b - a) - 2 crop, W - 2 crop]
+    # rows of the cropped output that belong to this band (full-image output row
+    # y_out = y - crop): the band's rows, minus the image-border ring
+    y_lo = max(plan.y0[rank], crop)
+    y_hi = min(plan.y1[rank], height - crop)
+    band = out[..., y_lo - a - crop:y_hi - a - crop, :].contiguous()
+    if world == 1:
+        return {"radiance": band}
+    counts = [min(plan.y1[r], height - crop) - max(plan.y0[r], crop) for r in range(world)]
+    rows_max = max(counts)
+    moved = band.movedim(-2, 0).contiguous()
+    padded = moved.new_zeros((rows_max,) + tuple(moved.shape[1:]))
+    padded[:moved.shape[0]].copy_(moved)
+    parts = moved.new_empty((world * rows_max,) + tuple(moved.shape[1:]))
+    dist.all_gather_into_tensor(parts, padded, group=group)
+    parts = parts.view((world, rows_max) + tuple(moved.shape[1:]))
+    full = th.cat([parts[r, :counts[r]] for r in range(world)], dim=0)
+    return {"radiance": full.movedim(0, -2).contiguous()}

@@ -110,3 +110,48 @@ def test_halo_exchange_gloo(world, shape):
         assert p.exitcode == 0
     for rank, res in results:
         assert all(res.values()), (rank, res)
+
+
+def _model_worker(rank, world, port, q):
+    """Tiled model inference (BASELINE config 5 logic) over gloo on CPU: the custom
+    ops are stood in for by the oracle, the convs are torch's CPU kernels."""
+    from sbmc_b200 import functions as funcs
+    from sbmc_b200 import models
+    from tests import kats
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        KW, S2G = kats.oracle_functions()
+        funcs.KernelWeighting, funcs.Scatter2Gather = KW, S2G
+        th.manual_seed(0)
+        net = models.Multisteps(5, 2, width=8, embedding_width=8, ksize=5, nsteps=1).eval()
+        g = th.Generator().manual_seed(1)
+        h, w, spp = 48 * world, 24, 2
+        samples = {"radiance": th.rand(1, spp, 3, h, w, generator=g),
+                   "features": th.randn(1, spp, 5, h, w, generator=g),
+                   "global_features": th.randn(1, 2, 1, 1, generator=g)}
+        with th.no_grad():
+            out = sharding.multisteps_forward_sharded(net, samples, rank, world, overlap=44)
+            ref = net(samples)
+        err = (out["radiance"] - ref["radiance"]).abs().max().item()
+        q.put((rank, {"shape": out["radiance"].shape == ref["radiance"].shape,
+                      "close": err < 1e-5}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tiled_model_inference_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in results:
+        assert all(res.values()), (rank, res)

@@ -1,4 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv1x1_chain_nhwc' -s 2 -c 2 -f -o gpurun_out/r1s_prof python tools/profile_chain.py > gpurun_out/r1s_ncu.log 2>&1
-tail -3 gpurun_out/r1s_ncu.log
+echo "== sweep dws"
+timeout 300 tools/sweep dws 2>&1 | grep -v "^mem" | tee gpurun_out/r1u_sweep.txt
+echo "== tiled 4K"
+for n in 1 2; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tools/tiled_inference.py --fast 2>&1 | grep "^{\|Error\|error" | tee gpurun_out/r1u_tiled$n.json | head -5
+done

@@ -142,8 +142,7 @@ int main(int argc, char **argv) {
     DDA(2, 4, 7) DDA(2, 2, 21) DDA(1, 8, 7) DDA(4, 2, 7) DDA(2, 6, 7) DDA(2, 4, 11)
   }
   if (all || !strcmp(which, "dws")) {
-    DWS(8, 2, 7, 1) DWS(8, 2, 7, 2) DWS(16, 1, 7, 1) DWS(16, 1, 7, 2) DWS(8, 2, 21, 1)
-    DWS(4, 4, 7, 1)
+    DWS(16, 1, 7, 2) DWS(16, 1, 7, 3) DWS(8, 2, 7, 3) DWS(8, 2, 7, 2) DWS(16, 1, 7, 0)
   }
   if (all || !strcmp(which, "s2g")) {
     S2G(8, 4, 3) S2G(4, 6, 3) S2G(8, 3, 7) S2G(4, 8, 3) S2G(16, 2, 3) S2G(2, 8, 7)

@@ -182,6 +182,20 @@ SBMC_API int sbmc_conv1x1_chain_nhwc_bf16(const void *xa, int64_t a_img_stride, 
                                  int out_nhwc_bf16, int64_t n_img, int64_t hw,
                                  void *stream);
 
+/* U-net decoder glue (sbmc/modules.py:314-319): out = cat([bilinear_upsample(low,
+ * size=(h, w), align_corners=False), skip], channels) in one pass on bf16
+ * channels-innermost tensors: low [n][hl][wl][cu], skip [n][h][w][cs],
+ * out [n][h][w][cu+cs]; cu and cs multiples of 8, 16-byte aligned pointers. */
+SBMC_API int sbmc_upsample_concat_nhwc_bf16(const void *low, const void *skip, void *out,
+                                   int64_t n, int hl, int wl, int h, int w, int cu,
+                                   int cs, void *stream);
+
+/* y = act(y + bias[channel]) in place on bf16 channels-innermost y [pixels][c]
+ * (the bias + activation after every U-net convolution, modules.py:176-181);
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.01); c multiple of 8. */
+SBMC_API int sbmc_bias_act_nhwc_bf16(void *y, const float *bias, int64_t pixels, int c, int act,
+                            void *stream);
+
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /
  * d_sum_w / d_weights cover exactly the band.  `data_ext` ([n][c][halo_top +

@@ -54,9 +54,10 @@ static int dweights_tuned(const float *data_ext, const float *d_output,
                           i64 w, int kh, int halo_top, int halo_bot,
                           cudaStream_t st) {
   constexpr int CH = KW < kChunk ? KW : kChunk;
-  // 16 rows per CTA, one CTA per SM, stores without L1 allocation
-  // (profiles/r1d_sweep.txt: 1.033 ms vs 1.052 ms for 8 rows / st.global.cs)
-  return run_bwd_dweights<C, KW, kRowsDw, 1, CH, 2>(
+  // 16 rows per CTA, one CTA per SM, st.global.cs (profiles/r1d_sweep.txt,
+  // r1u_sweep.txt: 1.022 ms vs 1.052 ms for 8 rows; L2 eviction hints on the
+  // operands / stores did not move the write rate: 1.033 ms)
+  return run_bwd_dweights<C, KW, kRowsDw, 1, CH, 0>(
       data_ext, d_output, d_sum_w, d_weights, n, h, w, kh, halo_top, halo_bot, st);
 }
 

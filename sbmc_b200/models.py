@@ -27,6 +27,7 @@ import torch as th
 import torch.nn as nn
 
 from . import conv1x1 as _conv1x1
+from . import unet_fast as _unet_fast
 from . import modules as ops
 from ._compat import crop_like, get_logger
 
@@ -200,7 +201,9 @@ class Multisteps(nn.Module):
             reduced = new.float().mean(1)                     # [bs, hw, 128]
             x = reduced.view(bs, h, w, 128).permute(0, 3, 1, 2)   # NCHW, channels_last memory
             unet = getattr(self, "propagation_{:02d}".format(step))
-            if getattr(self, "bf16_unet", False):
+            if getattr(self, "bf16_unet", False) and _unet_fast.supports(unet):
+                y = _unet_fast.autoencoder_forward(unet, x)   # bf16 channels_last
+            elif getattr(self, "bf16_unet", False):
                 with th.autocast("cuda", dtype=th.bfloat16):
                     y = unet(x)
             else:

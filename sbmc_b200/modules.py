@@ -217,9 +217,38 @@ class Autoencoder(nn.Module):
             if self.is_last:
                 return left
             coarse = self.next_level(self.downsample(left))
+            if _fused_upsample_ok(coarse, left):
+                return self.right(_upsample_concat(coarse, left))
             up = F.interpolate(coarse, size=left.shape[-2:], mode="bilinear",
                                align_corners=False)
             return self.right(th.cat([up, left], 1))
+
+
+def _fused_upsample_ok(coarse, left):
+    """bf16 channels_last CUDA tensors that need no gradient (the inference
+    pipeline): upsample + concat run as one pass (csrc/unet_ops.cu)."""
+    if th.is_grad_enabled() and (coarse.requires_grad or left.requires_grad):
+        return False
+    for t in (coarse, left):
+        if not (t.is_cuda and t.dtype == th.bfloat16 and t.dim() == 4 and t.shape[1] % 8 == 0
+                and t.is_contiguous(memory_format=th.channels_last)):
+            return False
+    return True
+
+
+def _upsample_concat(coarse, left):
+    from . import _lib
+    n, cu, hl, wl = coarse.shape
+    _, cs, h, w = left.shape
+    out = th.empty((n, cu + cs, h, w), device=left.device, dtype=th.bfloat16,
+                   memory_format=th.channels_last)
+    lib = _lib.load()
+    with th.cuda.device(left.device):
+        rc = lib.sbmc_upsample_concat_nhwc_bf16(
+            coarse.data_ptr(), left.data_ptr(), out.data_ptr(), n, hl, wl, h, w, cu, cs,
+            th.cuda.current_stream(left.device).cuda_stream)
+    _lib.check(rc, "upsample_concat")
+    return out
 
 
 def _ksize(k2):

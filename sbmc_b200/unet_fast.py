@@ -1,0 +1,116 @@
+"""bf16 channels_last inference path of the U-net (`modules.Autoencoder`,
+sbmc/modules.py:195-320): cuDNN runs the 3x3 convolutions (library GEMMs) on
+cached bf16 channels_last weights with the weight normalization folded in; the
+glue around them is ours -- bias + activation in one in-place pass and bilinear
+upsample + skip concatenation in one pass (csrc/unet_ops.cu) -- instead of eager
+PyTorch's broadcast add, activation, interpolate and cat kernels.
+"""
+import torch as th
+import torch.nn.functional as F
+
+from . import _lib
+
+__all__ = ["supports", "autoencoder_forward"]
+
+_ACT = {th.nn.ReLU: 1, th.nn.LeakyReLU: 2}
+
+
+def _chain_layers(chain):
+    """[(conv, act_code)] of a ConvChain without normalization layers, or None."""
+    layers = []
+    kids = list(chain.named_children())
+    for name, m in kids:
+        if name.startswith("layer_"):
+            seq = m.layer
+            if len(seq) != 2 or type(seq[1]) not in _ACT:
+                return None
+            if isinstance(seq[1], th.nn.LeakyReLU) and abs(seq[1].negative_slope - 0.01) > 1e-12:
+                return None
+            layers.append((seq[0], _ACT[type(seq[1])]))
+        elif name == "prediction":
+            layers.append((m, 0))
+        elif name == "output_activation":
+            if type(m) not in _ACT or not layers:
+                return None
+            if isinstance(m, th.nn.LeakyReLU) and abs(m.negative_slope - 0.01) > 1e-12:
+                return None
+            layers[-1] = (layers[-1][0], _ACT[type(m)])
+        else:
+            return None
+    for conv, _ in layers:
+        if not isinstance(conv, th.nn.Conv2d) or conv.bias is None or conv.groups != 1 \
+                or conv.out_channels % 8 or conv.stride != (1, 1) or conv.dilation != (1, 1):
+            return None
+    return layers
+
+
+def _levels(level):
+    while level is not None:
+        yield level
+        level = None if level.is_last else level.next_level
+
+
+def supports(autoencoder):
+    try:
+        for lvl in _levels(autoencoder.net):
+            if _chain_layers(lvl.left) is None:
+                return False
+            if not lvl.is_last:
+                if _chain_layers(lvl.right) is None or not isinstance(lvl.downsample, th.nn.MaxPool2d):
+                    return False
+        return True
+    except AttributeError:
+        return False
+
+
+def _prepared(conv):
+    """(bf16 channels_last weight with weight-norm folded, fp32 bias), cached."""
+    ver = tuple((p.data_ptr(), p._version) for p in conv.parameters())
+    cached = getattr(conv, "_sbmc_b200_fast", None)
+    if cached is not None and cached[0] == ver:
+        return cached[1], cached[2]
+    if hasattr(conv, "weight_g") and hasattr(conv, "weight_v"):
+        w = th._weight_norm(conv.weight_v, conv.weight_g, 0)
+    else:
+        w = conv.weight
+    w = w.detach().to(th.bfloat16).contiguous(memory_format=th.channels_last)
+    b = conv.bias.detach().float().contiguous()
+    object.__setattr__(conv, "_sbmc_b200_fast", (ver, w, b))
+    return w, b
+
+
+def _bias_act_(y, bias, act):
+    n, c, h, w = y.shape
+    lib = _lib.load()
+    with th.cuda.device(y.device):
+        rc = lib.sbmc_bias_act_nhwc_bf16(y.data_ptr(), bias.data_ptr(), n * h * w, c, act,
+                                         th.cuda.current_stream(y.device).cuda_stream)
+    _lib.check(rc, "bias_act")
+    return y
+
+
+def _chain(chain, x):
+    for conv, act in _chain_layers(chain):
+        w, b = _prepared(conv)
+        x = F.conv2d(x, w, None, conv.stride, conv.padding)
+        if not x.is_contiguous(memory_format=th.channels_last):
+            x = x.contiguous(memory_format=th.channels_last)
+        _bias_act_(x, b, act)
+    return x
+
+
+def _level(level, x):
+    from .modules import _upsample_concat
+    left = _chain(level.left, x)
+    if level.is_last:
+        return left
+    coarse = _level(level.next_level, level.downsample(left))
+    return _chain(level.right, _upsample_concat(coarse, left))
+
+
+def autoencoder_forward(autoencoder, x):
+    """x: [n, c, h, w] (any float dtype; converted to bf16 channels_last) ->
+    bf16 channels_last [n, c_out, h, w].  Inference only."""
+    x = x.to(th.bfloat16).contiguous(memory_format=th.channels_last)
+    with th.no_grad():
+        return _level(autoencoder.net, x)

@@ -360,3 +360,45 @@ def test_fused_progressive_backward_matches_composed(shape, loss_kind):
     assert (ka - kb).abs().max().item() <= 1e-4 * scale_k, (ka - kb).abs().max().item() / scale_k
     assert ((ka - kb).norm() / kb.norm()).item() <= 1e-5
     assert ((ra - rb).norm() / rb.norm()).item() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 16, 8, 5, 7, 10, 14), (1, 256, 128, 45, 80, 90, 160),
+                                   (1, 8, 24, 3, 3, 7, 5)])
+def test_fused_upsample_concat_matches_torch(shape):
+    """cat([F.interpolate(coarse, size, bilinear), left], 1) in one pass (bf16 channels_last)."""
+    n, cu, cs, hl, wl, h, w = shape
+    th.manual_seed(0)
+    coarse = th.randn(n, cu, hl, wl, device="cuda").to(th.bfloat16).contiguous(
+        memory_format=th.channels_last)
+    left = th.randn(n, cs, h, w, device="cuda").to(th.bfloat16).contiguous(
+        memory_format=th.channels_last)
+    assert modules._fused_upsample_ok(coarse, left)
+    got = modules._upsample_concat(coarse, left)
+    up = F.interpolate(coarse.float(), size=(h, w), mode="bilinear", align_corners=False)
+    assert got.shape == (n, cu + cs, h, w)
+    assert th.equal(got[:, cu:], left)
+    # bf16 rounding of the interpolated value: half an ulp
+    assert th.allclose(got[:, :cu].float(), up, rtol=2 ** -8, atol=1e-6)
+    assert not modules._fused_upsample_ok(coarse.float(), left)
+
+
+@pytest.mark.gpu
+def test_unet_fast_path_matches_fp32_module():
+    """The bf16 channels_last U-net path (cuDNN convs on cached folded weights +
+    our bias/activation and upsample/concat kernels) against the fp32 module."""
+    from sbmc_b200 import unet_fast
+    th.manual_seed(0)
+    net = modules.Autoencoder(16, 16, num_levels=3, increase_factor=2.0, num_convs=3, width=16,
+                              ksize=3, output_type="leaky_relu", pooling="max").cuda().eval()
+    with th.no_grad():
+        for prm in net.parameters():
+            prm.add_(0.05 * th.randn_like(prm))
+    assert unet_fast.supports(net)
+    x = th.randn(2, 16, 36, 52, device="cuda")
+    with th.no_grad():
+        ref = net(x)
+        got = unet_fast.autoencoder_forward(net, x)
+    assert got.dtype == th.bfloat16 and got.shape == ref.shape
+    assert ((got.float() - ref).norm() / ref.norm()).item() < 3e-2
+    assert not unet_fast.supports(modules.Autoencoder(16, 16, normalize=True))

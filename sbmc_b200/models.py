@@ -198,7 +198,9 @@ class Multisteps(nn.Module):
                 _conv1x1.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
                                             gf=gf if step == 0 else None, out=new[:, sp])
             feats, ca = new, 128
-            reduced = new.float().mean(1)                     # [bs, hw, 128]
+            reduced = new.mean(1, dtype=th.float32)           # [bs, hw, 128]
+            if getattr(self, "bf16_unet", False):
+                reduced = reduced.to(th.bfloat16)
             x = reduced.view(bs, h, w, 128).permute(0, 3, 1, 2)   # NCHW, channels_last memory
             unet = getattr(self, "propagation_{:02d}".format(step))
             if getattr(self, "bf16_unet", False) and _unet_fast.supports(unet):

@@ -8,6 +8,7 @@
 // whole on the device; a band addresses it through the row-band launchers
 // (halo_top = y0, halo_bot = H - y1), the same launchers that serve multi-GPU
 // H-sharding.  There is no CPU arithmetic in this file.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -99,9 +100,16 @@ static int ensure(int idx, size_t bytes, float **out) {
   return SBMC_OK;
 }
 
-// rows per band: ~64 MB of weights per band, a multiple of 8 rows
+// rows per band: ~256 MB of weights per band (SBMC_HOST_BAND_MB overrides; measured
+// 14.1 vs 13.6 Msamples/s end to end against 64 MB, profiles/r1y_e2e_band.txt), a
+// multiple of 8 rows
 static i64 band_rows(i64 h, i64 w, i64 taps) {
-  i64 hb = (64ll << 20) / (taps * w * 4);
+  static const i64 band_mb = [] {
+    const char *e = getenv("SBMC_HOST_BAND_MB");
+    const long v = e ? atol(e) : 0;
+    return (i64)(v > 0 && v <= 4096 ? v : 256);
+  }();
+  i64 hb = (band_mb << 20) / (taps * w * 4);
   hb = hb / 8 * 8;
   if (hb < 8) hb = 8;
   if (hb > h) hb = h;

@@ -402,3 +402,26 @@ def test_unet_fast_path_matches_fp32_module():
     assert got.dtype == th.bfloat16 and got.shape == ref.shape
     assert ((got.float() - ref).norm() / ref.norm()).item() < 3e-2
     assert not unet_fast.supports(modules.Autoencoder(16, 16, normalize=True))
+
+
+@pytest.mark.gpu
+def test_kpcn_forward_gpu_matches_oracle_backed_cpu(monkeypatch):
+    """KPCN (sbmc/models.py:221-291): the second caller of KernelWeighting (gather
+    kernels + softmax), GPU ops against the oracle-backed CPU run."""
+    monkeypatch.setattr(th.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(th.backends.cuda.matmul, "allow_tf32", False)
+    th.manual_seed(0)
+    net = models.KPCN(4, ksize=5, depth=3, width=8).cuda().eval()
+    h = w = 36
+    data = {"kpcn_diffuse_in": th.randn(2, 4, h, w), "kpcn_specular_in": th.randn(2, 4, h, w),
+            "kpcn_diffuse_buffer": th.rand(2, 3, h, w), "kpcn_specular_buffer": th.rand(2, 3, h, w),
+            "kpcn_albedo": th.rand(2, 3, h, w)}
+    with th.no_grad():
+        got = net({k: v.cuda() for k, v in data.items()})
+    KW, S2G = kats.oracle_functions()
+    monkeypatch.setattr(funcs, "KernelWeighting", KW)
+    monkeypatch.setattr(funcs, "Scatter2Gather", S2G)
+    with th.no_grad():
+        ref = net.cpu()(data)
+    for key in ("radiance", "diffuse", "specular"):
+        assert th.allclose(got[key].cpu(), ref[key], rtol=1e-4, atol=1e-5), key

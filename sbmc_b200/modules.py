@@ -278,6 +278,14 @@ class KernelApply(nn.Module):
         (output [bs, chans, h, w], sum_w [bs, 1, h, w])."""
         bs, k2, h, w = kernels.shape
         k = _ksize(k2)
+        if self.softmax and not self.splat and k * k == k2 and \
+                _splat.fused_available(data, kernels):
+            # inference: softmax over the taps + weighting in one pass over the
+            # logits (the fused splat kernel in gather mode); the softmax weights
+            # of a pixel sum to one by construction
+            sum_r, sum_w, _ = _splat.progressive_splat_update(
+                data.float(), kernels.float(), None, None, None, False)
+            return sum_r / sum_w, th.ones_like(sum_w)
         # the custom ops are fp32 (reduced-precision convs may feed them under autocast)
         kernels = kernels.float().contiguous().view(bs, k, k, h, w)
         data = data.float()

@@ -7,6 +7,10 @@ relative (tests/util.py states the exact form); Scatter2Gather bit-exact.
 import glob
 import os
 
+# small host bands so that the multi-band streaming pipeline is exercised at test
+# sizes (read once by the library, before its first host-buffer call)
+os.environ.setdefault("SBMC_HOST_BAND_MB", "16")
+
 import numpy as np
 import pytest
 import torch as th
@@ -320,3 +324,32 @@ def test_config2_call_properties():
         x0, x1 = max(0, -sx), min(w, w - sx)
         want[:, y0:y1, x0:x1] = src[:, y0 + sy:y1 + sy, x0 + sx:x1 + sx]
         assert th.equal(gather[:, dy_, dx_].view(th.int32), want.view(th.int32))
+
+
+def test_random_small_shapes_vs_oracle():
+    """Seeded random shapes beyond the fixed list: ragged sizes, even / non-square
+    kernels, 1..6 channels; both device implementations against the oracle."""
+    import random
+    rng = random.Random(1)
+    for it in range(16):
+        kh, kw = rng.randint(1, 8), rng.randint(1, 8)
+        c = rng.randint(1, 6)
+        h, w = rng.randint(1, 24), rng.choice([4, 8, 12, 20, 36, 132, rng.randint(1, 50)])
+        n = rng.randint(1, 3)
+        data, weights, d_output, d_sum_w = make_inputs(n, c, h, w, kh, kw, seed=100 + it)
+        mo, ms, mdd, mdw = kw_magnitudes(data, weights, d_output, d_sum_w)
+        ro, rs = oracle.kernel_weighting(data, weights)
+        rdd, rdw = oracle.kernel_weighting_grad(data, weights, d_output, d_sum_w)
+        rg = oracle.scatter2gather(weights)
+        for flag in (0, 1):
+            prev = _lib.force_generic(flag)
+            try:
+                out, sum_w, d_data, d_weights, gather = run_cuda(data, weights, d_output, d_sum_w)
+            finally:
+                _lib.force_generic(prev)
+            what = "shape %s path %d" % ((n, c, h, w, kh, kw), flag)
+            assert_close_sum(out, ro, mo, what + " output")
+            assert_close_sum(sum_w, rs, ms, what + " sum_w")
+            assert_close_sum(d_data, rdd, mdd, what + " d_data")
+            assert_close_sum(d_weights, rdw, mdw, what + " d_weights")
+            assert np.array_equal(gather.cpu().numpy().view(np.uint32), rg.numpy().view(np.uint32)), what

@@ -425,3 +425,47 @@ def test_kpcn_forward_gpu_matches_oracle_backed_cpu(monkeypatch):
         ref = net.cpu()(data)
     for key in ("radiance", "diffuse", "specular"):
         assert th.allclose(got[key].cpu(), ref[key], rtol=1e-4, atol=1e-5), key
+
+
+@pytest.mark.gpu
+def test_kernel_apply_softmax_gather_fused_matches_composed():
+    """KPCN's KernelApply(softmax=True, splat=False): one fused pass without grad
+    against softmax + KernelWeighting with grad enabled."""
+    th.manual_seed(5)
+    bs, c, h, w, k = 2, 3, 20, 36, 5
+    data = th.rand(bs, c, h, w, device="cuda")
+    logits = 3 * th.randn(bs, k * k, h, w, device="cuda")
+    mod = modules.KernelApply(softmax=True, splat=False)
+    with th.no_grad():
+        out_f, sw_f = mod(data, logits)
+    out_c, sw_c = mod(data, logits.clone().requires_grad_(True))
+    assert th.allclose(out_f, out_c.detach(), rtol=2e-5, atol=1e-6)
+    assert th.allclose(sw_f, sw_c.detach(), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_random_small_shapes_fused_splat():
+    """Seeded random shapes (ragged widths, K in 3..9, C in 1..5): the fused splat
+    (tuned or generic kernel, whichever serves the shape) against the composed chain."""
+    import random
+    rng = random.Random(0)
+    for _ in range(12):
+        k = rng.choice([3, 5, 7, 9])
+        c = rng.choice([1, 3, 3, 5])
+        h, w = rng.randint(k, 30), rng.randint(k, 70)
+        bs = rng.randint(1, 2)
+        splat = rng.random() < 0.7
+        th.manual_seed(h * w)
+        rad = th.rand(bs, 2, c, h, w, device="cuda")
+        logits = 3 * th.randn(bs, 2, k * k, h, w, device="cuda")
+        fused = modules.ProgressiveKernelApply(splat=splat)
+        comp = modules.ProgressiveKernelApply(splat=splat)
+        comp.fused = False
+        a = b = (None, None, None)
+        with th.no_grad():
+            for sp in range(2):
+                a = fused(rad[:, sp], logits[:, sp].clone(), *a)
+                b = comp(rad[:, sp], logits[:, sp].clone(), *b)
+        assert th.equal(a[2], b[2]), (k, c, h, w, splat)
+        assert th.allclose(a[1], b[1], rtol=1e-4), (k, c, h, w, splat)
+        assert th.allclose(a[0], b[0], rtol=1e-4, atol=1e-5), (k, c, h, w, splat)

@@ -44,6 +44,29 @@ __global__ void __launch_bounds__(256) read_stream_kernel(const float *p, size_t
   if (acc == 123.456f) *out = acc;   // never true: keeps the loads alive
 }
 
+// Synthetic write-pattern probes (no arithmetic): which store pattern over the
+// K*K-plane volume reaches the memset rate?  CTA = ROWS warps; warp r owns row
+// Y0 + r and, per tap, writes SEGS consecutive 512-byte segments of that row.
+template <int ROWS, int SEGS>
+__global__ void __launch_bounds__(ROWS * 32)
+write_pattern_kernel(float *dW, int H, int W, int taps, int xtiles, int ytiles) {
+  const int xt = blockIdx.x % xtiles;
+  const unsigned r = blockIdx.x / xtiles;
+  const int yt = r % ytiles, n = r / ytiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = yt * ROWS + warp;
+  const int x0 = xt * SEGS * 128 + 4 * lane;
+  if (y >= H) return;
+  const long long plane = (long long)H * W;
+  float *wp = dW + (long long)n * taps * plane + (long long)y * W + x0;
+  const float4 v = make_float4(1.f, 2.f, 3.f, (float)lane);
+  for (int t = 0; t < taps; ++t) {
+#pragma unroll
+    for (int s = 0; s < SEGS; ++s)
+      if (x0 + s * 128 < W) stg_stream(wp + (long long)t * plane + s * 128, v);
+  }
+}
+
 struct Ctx {
   i64 n = 4, h = 720, w = 1280;
   int k = 21;
@@ -144,6 +167,17 @@ int main(int argc, char **argv) {
     read_stream_kernel<<<148 * 16, 256, 0, c.st>>>(c.wt, vol / 4, c.out);
     return 0;
   });
+#define WPAT(ROWS, SEGS)                                                      \
+  time_it(c, "write pattern rows=" #ROWS " segs=" #SEGS, 4.0 * 441, [&] {      \
+    const int xt = (int)ceil_div(c.w, SEGS * 128), yt = (int)ceil_div(c.h, ROWS); \
+    write_pattern_kernel<ROWS, SEGS><<<(unsigned)(xt * yt * c.n), ROWS * 32, 0, c.st>>>( \
+        c.dwt, (int)c.h, (int)c.w, c.k * c.k, xt, yt);                        \
+    return 0;                                                                 \
+  });
+  if (!strcmp(which, "wpat")) {
+    WPAT(16, 1) WPAT(8, 1) WPAT(8, 2) WPAT(4, 4) WPAT(8, 5) WPAT(2, 10) WPAT(1, 10) WPAT(4, 10)
+    WPAT(16, 2) WPAT(4, 2)
+  }
   const bool all = !strcmp(which, "all");
   if (all || !strcmp(which, "fwd")) {
     FWD(8, 2, 7) FWD(8, 2, 11) FWD(8, 2, 21) FWD(8, 3, 3) FWD(8, 3, 7) FWD(8, 1, 21)

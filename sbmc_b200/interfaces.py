@@ -1,7 +1,10 @@
-"""Training-step glue, API-compatible with the reference's
-``sbmc/interfaces.py:35-132`` (``SampleBasedDenoiserInterface``: forward /
-backward / init_validation / update_validation) without the external ``ttools``
-base class.  It is a caller of the hot path (config 4 of BASELINE.json)."""
+"""One optimisation step of the denoiser: the caller behind BASELINE.json's
+config 4.  Same public surface as the reference's training glue
+(``sbmc/interfaces.py:35-132``: ``forward`` / ``backward`` / ``init_validation`` /
+``update_validation``, Adam on the model parameters, tonemapped relative MSE as
+the loss, gradient-norm clip at 1000, non-finite-loss guard) without the external
+``ttools.ModelInterface`` base class.
+"""
 import math
 
 import torch as th
@@ -12,58 +15,65 @@ from ._compat import crop_like, get_logger
 __all__ = ["SampleBasedDenoiserInterface"]
 
 LOG = get_logger(__name__)
+_GRAD_CLIP = 1000
 
 
 class SampleBasedDenoiserInterface(object):
-    """Args: model (nn.Module), lr (float), cuda (bool)."""
+    """model: nn.Module taking / returning dicts; lr: Adam step size; cuda: move
+    the model (and every batch) to the GPU."""
 
     def __init__(self, model, lr=1e-4, cuda=False):
+        self.model = model.cuda() if cuda else model
         self.device = "cuda" if cuda else "cpu"
-        self.model = model
         self.loss_fn = losses.TonemappedRelativeMSE()
         self.rmse_fn = losses.RelativeMSE()
-        if cuda:
-            self.model.cuda()
         self.optimizer = th.optim.Adam(self.model.parameters(), lr=lr)
 
+    # -- helpers -----------------------------------------------------------------
+    def _to_device(self, batch):
+        for key, value in batch.items():
+            if isinstance(value, th.Tensor):
+                batch[key] = value.to(self.device)
+        return batch
+
+    def _scores(self, batch, fwd):
+        """(loss, rmse) tensors of a forward result against the batch's target,
+        cropped to the (smaller) network output."""
+        out = fwd["radiance"]
+        tgt = crop_like(batch["target_image"], out)
+        return self.loss_fn(out, tgt), out, tgt
+
+    # -- ttools.ModelInterface protocol ---------------------------------------------
     def forward(self, batch):
-        for k in batch:
-            if isinstance(batch[k], th.Tensor):
-                batch[k] = batch[k].to(self.device)
-        return self.model(batch)
+        return self.model(self._to_device(batch))
 
     def backward(self, batch, fwd):
         self.optimizer.zero_grad()
-        out = fwd["radiance"]
-        tgt = crop_like(batch["target_image"], out)
-        loss = self.loss_fn(out, tgt)
+        loss, out, tgt = self._scores(batch, fwd)
         loss.backward()
         value = loss.item()
-        if math.isinf(value):
-            LOG.error("Loss is infinite, there might be outliers in the data.")
-            raise RuntimeError("Infinite loss at train time.")
-        if math.isnan(value):
-            LOG.error("NaN in the loss, there might be outliers in the data.")
-            raise RuntimeError("NaN loss at train time.")
-        clip = 1000
-        actual = th.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
-        if actual > clip:
-            LOG.info("Clipped gradients {} -> {}".format(clip, actual))
+        if not math.isfinite(value):      # outliers in the data show up here
+            kind = "NaN" if math.isnan(value) else "Infinite"
+            LOG.error("%s loss, there might be outliers in the data.", kind)
+            raise RuntimeError("%s loss at train time." % kind)
+        norm = th.nn.utils.clip_grad_norm_(self.model.parameters(), _GRAD_CLIP)
+        if norm > _GRAD_CLIP:
+            LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, float(norm))
         self.optimizer.step()
         with th.no_grad():
-            rmse = self.rmse_fn(out, tgt)
-        return {"loss": value, "rmse": rmse.item()}
+            rmse = self.rmse_fn(out, tgt).item()
+        return {"loss": value, "rmse": rmse}
 
     def init_validation(self):
         return {"loss": 0.0, "rmse": 0.0, "n": 0}
 
     def update_validation(self, batch, fwd, running):
+        """Running means weighted by the batch size (it may vary)."""
         with th.no_grad():
-            out = fwd["radiance"]
-            tgt = crop_like(batch["target_image"], out)
-            loss = self.loss_fn(out, tgt).item()
-            rmse = self.rmse_fn(out, tgt).item()
+            loss, out, tgt = self._scores(batch, fwd)
+            loss, rmse = loss.item(), self.rmse_fn(out, tgt).item()
         b = out.shape[0]
         n = running["n"] + b
-        return {"loss": running["loss"] - (1.0 / n) * (running["loss"] - b * loss),
-                "rmse": running["rmse"] - (1.0 / n) * (running["rmse"] - b * rmse), "n": n}
+        step = 1.0 / n
+        return {"loss": running["loss"] - step * (running["loss"] - b * loss),
+                "rmse": running["rmse"] - step * (running["rmse"] - b * rmse), "n": n}

@@ -196,6 +196,12 @@ SBMC_API int sbmc_upsample_concat_nhwc_bf16(const void *low, const void *skip, v
 SBMC_API int sbmc_bias_act_nhwc_bf16(void *y, const float *bias, int64_t pixels, int c, int act,
                             void *stream);
 
+/* fp32 channel planes x [n][c][hw] -> bf16 channels-innermost y [n][hw][cpad],
+ * zero-padded to cpad (multiple of 8) channels; `*_img_stride` in elements. */
+SBMC_API int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void *y,
+                           int64_t y_img_stride, int64_t n, int c, int64_t hw, int cpad,
+                           void *stream);
+
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /
  * d_sum_w / d_weights cover exactly the band.  `data_ext` ([n][c][halo_top +

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sbmc_upsample_concat_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_bias_act_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _ptr]),
+    "sbmc_nchw_to_nhwc_bf16": (_int, [_ptr, _i64, _ptr, _i64, _i64, _int, _i64, _int, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),

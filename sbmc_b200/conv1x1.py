@@ -150,6 +150,19 @@ def to_nhwc_bf16(x, channels=_HID):
     """[..., c, h, w] fp32 -> [..., h*w, channels] bf16 (zero-padded channels)."""
     c, h, w = x.shape[-3:]
     lead = x.shape[:-3]
+    if x.is_cuda and x.dtype == th.float32 and channels % 8 == 0 and c <= channels:
+        x = x.contiguous()
+        out = th.empty(lead + (h * w, channels), device=x.device, dtype=th.bfloat16)
+        n = 1
+        for d in lead:
+            n *= d
+        lib = _lib.load()
+        with th.cuda.device(x.device):
+            rc = lib.sbmc_nchw_to_nhwc_bf16(
+                x.data_ptr(), c * h * w, out.data_ptr(), h * w * channels, n, c, h * w,
+                channels, th.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "nchw_to_nhwc")
+        return out
     out = x.new_zeros(lead + (h * w, channels), dtype=th.bfloat16)
     out[..., :c] = x.reshape(lead + (c, h * w)).transpose(-1, -2)
     return out

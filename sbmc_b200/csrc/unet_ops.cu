@@ -183,3 +183,68 @@ extern "C" int sbmc_bias_act_nhwc_bf16(void *y, const float *bias, int64_t pixel
   note_path(1);
   return SBMC_OK;
 }
+
+// ---------------------------------------------------------------------------
+// fp32 [n][c][hw] (channel planes) -> bf16 [n][hw][cpad] (channels innermost,
+// zero-padded to cpad): the entry of the inference pipeline for the raw sample
+// features (sbmc/models.py:120-129).  One thread per pixel: per channel a warp
+// reads 32 consecutive floats of one plane (coalesced), and every thread writes
+// its pixel's cpad channels as contiguous 16-byte chunks.
+// ---------------------------------------------------------------------------
+namespace sbmc {
+
+__global__ void __launch_bounds__(128)
+nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64 n, int c,
+                         i64 hw, i64 x_img, i64 y_img8, int cpad8) {
+  const i64 tiles = (hw + 127) / 128;
+  for (i64 t = blockIdx.x; t < n * tiles; t += gridDim.x) {
+    const i64 img = t / tiles;
+    const i64 p = (t - img * tiles) * 128 + threadIdx.x;
+    if (p >= hw) continue;
+    const float *src = x + img * x_img + p;
+    uint4 *dst = y + img * y_img8 + p * cpad8;
+#pragma unroll 2
+    for (int c8 = 0; c8 < cpad8; ++c8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = c8 * 8 + j;
+        v[j] = ch < c ? __ldg(src + (i64)ch * hw) : 0.f;
+      }
+      uint4 q;
+      __nv_bfloat162 *o = reinterpret_cast<__nv_bfloat162 *>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      dst[c8] = q;
+    }
+  }
+}
+
+}  // namespace sbmc
+
+extern "C" int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void *y,
+                                      int64_t y_img_stride, int64_t n, int c, int64_t hw,
+                                      int cpad, void *stream) {
+  using namespace sbmc;
+  if (n < 0 || c < 1 || hw < 0 || cpad < c || cpad % 8) {
+    set_error("nchw_to_nhwc: invalid arguments");
+    return SBMC_EINVAL;
+  }
+  if (n == 0 || hw == 0) return SBMC_OK;
+  if (!x || !y || (reinterpret_cast<uintptr_t>(y) & 15) || y_img_stride % 8) {
+    set_error("nchw_to_nhwc: null or misaligned pointer");
+    return SBMC_EINVAL;
+  }
+  const i64 tiles = n * ((hw + 127) / 128);
+  i64 blocks = tiles < (i64)num_sms() * 16 ? tiles : (i64)num_sms() * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    KernelTimer timer(SBMC_KERNEL_OTHER, st);
+    nchw_to_nhwc_bf16_kernel<<<(unsigned)blocks, 128, 0, st>>>(
+        x, static_cast<uint4 *>(y), n, c, hw, x_img_stride, y_img_stride / 8, cpad / 8);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  note_path(1);
+  return SBMC_OK;
+}

@@ -27,7 +27,7 @@ from . import _lib
 
 __all__ = ["BandPlan", "exchange_halo", "reduce_halo", "kernel_weighting_fwd_sharded",
            "kernel_weighting_bwd_sharded", "ShardedKernelWeighting", "gather_bands",
-           "multisteps_forward_sharded"]
+           "multisteps_forward_sharded", "multisteps_forward_halo"]
 
 
 class BandPlan:
@@ -39,12 +39,13 @@ class BandPlan:
     forward / d_weights and the rows reached by d_data for odd and even K.
     """
 
-    def __init__(self, height, world, kh, kw=None):
+    def __init__(self, height, world, kh, kw=None, pad=None):
         if height < world:
             raise ValueError("cannot split %d rows over %d ranks" % (height, world))
         self.height, self.world, self.kh, self.kw = height, world, kh, kw or kh
         c0 = (kh - 1) // 2
-        self.pad = max(c0, kh - 1 - c0)
+        # `pad` overrides the halo width (e.g. the receptive field of a U-net)
+        self.pad = max(c0, kh - 1 - c0) if pad is None else pad
         base, extra = divmod(height, world)
         self.y0, self.y1 = [], []
         y = 0
@@ -266,6 +267,82 @@ def multisteps_forward_sharded(model, samples, rank, world, overlap=144, group=N
     counts = [min(plan.y1[r], height - crop) - max(plan.y0[r], crop) for r in range(world)]
     rows_max = max(counts)
     moved = band.movedim(-2, 0).contiguous()
+    padded = moved.new_zeros((rows_max,) + tuple(moved.shape[1:]))
+    padded[:moved.shape[0]].copy_(moved)
+    parts = moved.new_empty((world * rows_max,) + tuple(moved.shape[1:]))
+    dist.all_gather_into_tensor(parts, padded, group=group)
+    parts = parts.view((world, rows_max) + tuple(moved.shape[1:]))
+    full = th.cat([parts[r, :counts[r]] for r in range(world)], dim=0)
+    return {"radiance": full.movedim(0, -2).contiguous()}
+
+
+def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None):
+    """Tiled inference with halo EXCHANGE instead of full overlap recompute
+    (inference pipeline of `Multisteps._forward_nhwc`, needs `model.bf16_chains`).
+
+    Per rank: the per-sample 1x1 chains, the kernel regressor and the fused splat
+    run on the band plus (K-1)/2 rows (everything a band pixel's K x K splat
+    neighbourhood needs); before each of the `nsteps` U-nets the ranks exchange
+    `unet_pad` rows of the pixel-domain tensor `reduced` with their neighbours
+    (one NCCL all-gather of the band edges per step, [bs, 128 ch, unet_pad, W]),
+    so the U-net sees real neighbour rows instead of recomputing them through the
+    whole network; `unet_pad` only has to cover ONE U-net's receptive field
+    (~39 px) because every step exchanges again.  Final all-gather of the bands.
+    Same result as the unsharded forward up to the U-net's zero padding at
+    distance >= unet_pad (exact when unet_pad covers the receptive field).
+    """
+    from . import conv1x1 as _c
+    from . import unet_fast as _u
+    from ._compat import crop_like
+    radiance, features = samples["radiance"], samples["features"]
+    bs, spp, nf, height, w = features.shape
+    k = model.ksize
+    crop = (k - 1) // 2
+    if unet_pad % 4 or not model._nhwc_pipeline_ok(nf):
+        raise ValueError("halo mode needs unet_pad % 4 == 0 and the 128-wide 1x1 chains")
+    plan = BandPlan(height, world, k)                 # K x K halo (splat)
+    uplan = BandPlan(height, world, k, pad=unet_pad)  # U-net halo
+    if any(y % 4 for y in plan.y0):
+        raise ValueError("band origins must be multiples of 4")
+    dev = th.device("cuda", th.cuda.current_device())
+    y0, y1 = plan.y0[rank], plan.y1[rank]
+    top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+    a, b = y0 - top, y1 + bot                          # rows of the chain / splat domain
+    rows_ext, rows = b - a, y1 - y0
+    rad = radiance[..., a:b, :].to(dev)
+    feats = _c.to_nhwc_bf16(features[..., a:b, :].to(dev))        # [bs, spp, rows_ext*w, 128]
+    gf = samples["global_features"].to(dev).reshape(bs, -1).float()
+    hw = rows_ext * w
+    prop, ca = None, nf
+    utop, ubot = uplan.halo_top(rank), uplan.halo_bot(rank)
+    for step in range(model.nsteps):
+        embed = getattr(model, "embedding_{:02d}".format(step))
+        new = feats.new_empty(bs, spp, hw, 128)
+        for sp in range(spp):
+            _c.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
+                                  gf=gf if step == 0 else None, out=new[:, sp])
+        feats, ca = new, 128
+        reduced = new.mean(1, dtype=th.float32).to(th.bfloat16)    # [bs, hw, 128]
+        band = reduced.view(bs, rows_ext, w * 128)[:, top:top + rows]
+        ext = exchange_halo(uplan, rank, band, group)              # [bs, utop+rows+ubot, w*128]
+        x = ext.view(bs, utop + rows + ubot, w, 128).permute(0, 3, 1, 2)
+        y = _u.autoencoder_forward(getattr(model, "propagation_{:02d}".format(step)), x)
+        y = y.permute(0, 2, 3, 1)[:, utop - top:utop + rows + bot]  # back to the ext rows
+        prop = y.to(th.bfloat16).contiguous().view(bs, hw, 128)
+    sum_r = sum_w = max_w = None
+    for sp in range(spp):
+        kernels = _c.chain_forward_nhwc(model.kernel_regressor, feats[:, sp], 128, xb=prop,
+                                        nhwc_out=False).view(bs, k * k, rows_ext, w)
+        sum_r, sum_w, max_w = model.kernel_update(
+            crop_like(rad[:, sp], kernels), kernels, sum_r, sum_w, max_w)
+    out = sum_r / (sum_w + model.eps)                  # [bs, 3, rows_ext, w]
+    y_lo, y_hi = max(y0, crop), min(y1, height - crop)
+    band_out = out[..., y_lo - a:y_hi - a, crop:w - crop].contiguous()
+    if world == 1:
+        return {"radiance": band_out}
+    counts = [min(plan.y1[r], height - crop) - max(plan.y0[r], crop) for r in range(world)]
+    rows_max = max(counts)
+    moved = band_out.movedim(-2, 0).contiguous()
     padded = moved.new_zeros((rows_max,) + tuple(moved.shape[1:]))
     padded[:moved.shape[0]].copy_(moved)
     parts = moved.new_empty((world * rows_max,) + tuple(moved.shape[1:]))

@@ -177,3 +177,15 @@ def test_nhwc_chain_strided_views():
         one = conv1x1.chain_forward_nhwc(reg, feats[:, 1].contiguous(), 128, xb=prop)
     assert th.equal(new[:, 2], one)
     assert (new[:, :2] == 0).all()
+
+
+@pytest.mark.gpu
+def test_to_nhwc_bf16_kernel_matches_torch():
+    th.manual_seed(6)
+    for shape in [(2, 3, 93, 9, 13), (1, 1, 128, 16, 32), (3, 5, 7, 11)]:
+        x = th.randn(*shape, device="cuda")
+        got = conv1x1.to_nhwc_bf16(x)
+        c, h, w = shape[-3:]
+        want = th.zeros(shape[:-3] + (h * w, 128), device="cuda", dtype=th.bfloat16)
+        want[..., :c] = x.reshape(shape[:-3] + (c, h * w)).transpose(-1, -2)
+        assert th.equal(got, want)

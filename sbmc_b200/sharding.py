@@ -39,21 +39,24 @@ class BandPlan:
     forward / d_weights and the rows reached by d_data for odd and even K.
     """
 
-    def __init__(self, height, world, kh, kw=None, pad=None):
-        if height < world:
+    def __init__(self, height, world, kh, kw=None, pad=None, align=1):
+        if height < world * align:
             raise ValueError("cannot split %d rows over %d ranks" % (height, world))
         self.height, self.world, self.kh, self.kw = height, world, kh, kw or kh
         c0 = (kh - 1) // 2
-        # `pad` overrides the halo width (e.g. the receptive field of a U-net)
+        # `pad` overrides the halo width (e.g. the receptive field of a U-net);
+        # `align` makes every band start on a multiple of `align` rows (the U-net's
+        # 2x2 poolings need band origins that are multiples of 4)
         self.pad = max(c0, kh - 1 - c0) if pad is None else pad
-        base, extra = divmod(height, world)
+        units = (height + align - 1) // align
+        base, extra = divmod(units, world)
         self.y0, self.y1 = [], []
         y = 0
         for r in range(world):
-            rows = base + (1 if r < extra else 0)
-            self.y0.append(y)
+            rows = (base + (1 if r < extra else 0)) * align
+            self.y0.append(min(y, height))
             y += rows
-            self.y1.append(y)
+            self.y1.append(min(y, height))
         if world > 1 and min(b - a for a, b in zip(self.y0, self.y1)) < self.pad:
             raise ValueError("bands (%d rows) are shorter than the halo (%d rows)"
                              % (base, self.pad))
@@ -246,10 +249,7 @@ def multisteps_forward_sharded(model, samples, rank, world, overlap=144, group=N
     crop = (model.ksize - 1) // 2
     if overlap % 4 or overlap < crop:
         raise ValueError("overlap must be a multiple of 4 and >= (K-1)/2")
-    plan = BandPlan(height, world, model.ksize)
-    if any(y % 4 for y in plan.y0):
-        raise ValueError("band origins must be multiples of 4 (H = %d over %d ranks)"
-                         % (height, world))
+    plan = BandPlan(height, world, model.ksize, align=4)
     a, b, top = model_band_rows(plan, rank, overlap)
     dev = th.device("cuda", th.cuda.current_device()) if th.cuda.is_available() \
         else radiance.device
@@ -300,10 +300,8 @@ def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None
     crop = (k - 1) // 2
     if unet_pad % 4 or not model._nhwc_pipeline_ok(nf):
         raise ValueError("halo mode needs unet_pad % 4 == 0 and the 128-wide 1x1 chains")
-    plan = BandPlan(height, world, k)                 # K x K halo (splat)
-    uplan = BandPlan(height, world, k, pad=unet_pad)  # U-net halo
-    if any(y % 4 for y in plan.y0):
-        raise ValueError("band origins must be multiples of 4")
+    plan = BandPlan(height, world, k, align=4)                 # K x K halo (splat)
+    uplan = BandPlan(height, world, k, pad=unet_pad, align=4)  # U-net halo
     dev = th.device("cuda", th.cuda.current_device())
     y0, y1 = plan.y0[rank], plan.y1[rank]
     top, bot = plan.halo_top(rank), plan.halo_bot(rank)

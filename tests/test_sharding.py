@@ -24,6 +24,13 @@ def test_band_plan():
     assert plan.pad == 2
     assert [plan.rows(r) for r in range(4)] == [26, 26, 26, 25]
     assert plan.y0 == [0, 26, 52, 78] and plan.y1[-1] == 103
+    uplan = sharding.BandPlan(2160, 8, 21, pad=64)   # U-net halo of the tiled model
+    assert uplan.pad == 64 and uplan.halo_top(0) == 0 and uplan.halo_bot(0) == 64
+    assert uplan.halo_top(7) == 64 and uplan.halo_bot(7) == 0
+    aplan = sharding.BandPlan(2160, 8, 21, align=4)  # 270 rows / rank is not a multiple of 4
+    assert [aplan.rows(r) for r in range(8)] == [272] * 4 + [268] * 4
+    assert all(y % 4 == 0 for y in aplan.y0) and aplan.y1[-1] == 2160
+    assert sharding.BandPlan(103, 4, 4, align=4).y1 == [28, 56, 80, 103]
     with pytest.raises(ValueError):
         sharding.BandPlan(3, 4, 3)
     with pytest.raises(ValueError):

@@ -47,6 +47,31 @@ def test_supports_and_prepare():
                                                   normalize=True))
 
 
+def test_prepare_nhwc_channel_mapping():
+    """Input channel order of a chain: [ca real channels | ngf broadcast features |
+    cb second-source channels]; the NHWC kernel sees xa padded to 128 channels and
+    the broadcast features folded into a per-image bias."""
+    chains = _chains()
+    emb0 = chains["embedding_00"]                       # 93 + 3 inputs
+    p = conv1x1._prepare_nhwc(emb0, 93, 0, 3)
+    w = conv1x1._effective_weight(conv1x1._convs(emb0)[0])
+    assert p.w1.shape == (128, 128) and p.w1_gf.shape == (128, 3)
+    assert th.equal(p.w1[:, :93], w[:, :93].to(th.bfloat16)) and (p.w1[:, 93:] == 0).all()
+    assert th.equal(p.w1_gf, w[:, 93:96])
+    reg = chains["kernel_regressor"]                    # 128 + 128 inputs
+    p = conv1x1._prepare_nhwc(reg, 128, 128, 0)
+    w = conv1x1._effective_weight(conv1x1._convs(reg)[0])
+    assert p.w1.shape == (128, 256) and th.equal(p.w1, w.to(th.bfloat16))
+    assert p.n3p == 448 and p.cout == 441 and p.act == 1
+    assert conv1x1._prepare_nhwc(reg, 128, 128, 0) is p
+    with pytest.raises(RuntimeError):
+        conv1x1._prepare_nhwc(reg, 100, 128, 0)
+    x = th.randn(2, 5, 3, 4)                            # CPU fallback of the layout change
+    y = conv1x1.to_nhwc_bf16(x, channels=8)
+    assert y.shape == (2, 12, 8) and (y[..., 5:] == 0).all()
+    assert th.equal(y[..., :5], x.reshape(2, 5, 12).transpose(1, 2).to(th.bfloat16))
+
+
 def _emulate(chain, x):
     """The chain with the kernel's rounding points: bf16 operands, fp32 accumulate."""
     p = conv1x1.prepare(chain)

@@ -30,8 +30,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "Msamples/s (spp*H*W) KernelWeighting fwd+bwd"
 UNIT = "Msamples/s"
+
+
+def _metric_name():
+    """BASELINE.json's metric string (the driver matches on it)."""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as fid:
+            return json.load(fid)["metric"]
+    except (OSError, ValueError, KeyError):
+        return ("Msamples/s (spp\u00d7H\u00d7W) KernelWeighting fwd+bwd @ spp=8 K=21 720p, "
+                "1/2/4/8 GPU")
+
+
+METRIC = _metric_name()
 
 
 def parse_args():

@@ -20,10 +20,11 @@
  * The arithmetic lives in the reference tree (Halide algorithm text); the code
  * generator that turns it into machine code is Halide v8.0.0, which is not in
  * /root/reference and cannot be installed here.  PARITY PIN: the reference's
- * analytic known-answer tests (tests/test_functions.py:43-208,
- * tests/test_modules.py:63-140) plus an independent float64 restatement
- * (oracle/numpy_ref.py).  Dense-random outputs of the Halide binary itself are
- * NOT available: "parity unpinned" for those beyond the KATs.
+ * own test files run unmodified against this oracle (tests/test_reference_suite.py:
+ * tests/test_functions.py, tests/test_modules.py of the reference), plus an
+ * independent float64 restatement (oracle/numpy_ref.py).  Dense-random outputs of
+ * the Halide binary itself are NOT available: "parity unpinned" for those beyond
+ * the known-answer tests.
  *
  * Numerics: fp32 multiply then fp32 add (compile with -ffp-contract=off),
  * reduction order ry outer / rx inner, sequential, exactly the RDom order of

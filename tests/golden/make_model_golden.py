@@ -35,6 +35,7 @@ def import_reference():
     from sbmc_b200 import _compat
     ttools = types.ModuleType("ttools")
     ttools.get_logger = _compat.get_logger
+    ttools.ModelInterface = object          # base class of sbmc/interfaces.py:35
     tmods = types.ModuleType("ttools.modules")
     timg = types.ModuleType("ttools.modules.image_operators")
     timg.crop_like = _compat.crop_like
@@ -52,7 +53,7 @@ def import_reference():
     sys.modules["sbmc.halide_ops"] = hops
     pkg.halide_ops = hops
     mods = {}
-    for name in ("functions", "modules", "models"):
+    for name in ("functions", "modules", "models", "losses", "interfaces"):
         spec = importlib.util.spec_from_file_location(
             "sbmc." + name, os.path.join(REFERENCE, "sbmc", name + ".py"))
         mod = importlib.util.module_from_spec(spec)
@@ -140,6 +141,25 @@ def main():
     out["kpcn"] = {"ctor": dict(n_in=4, ksize=5, depth=3, width=8),
                    "state_dict": {k_: v.clone() for k_, v in kpcn.state_dict().items()},
                    "data": kdata, "out": {k_: v for k_, v in ko.items()}}
+
+    # -- two optimisation steps through the reference's training interface ------------
+    th.manual_seed(10)
+    net = ref["models"].Multisteps(6, 2, width=8, embedding_width=8, ksize=3, nsteps=1)
+    randomize(net, g)
+    init = {k_: v.clone() for k_, v in net.state_dict().items()}
+    iface = ref["interfaces"].SampleBasedDenoiserInterface(net, lr=1e-3, cuda=False)
+    batch = {"radiance": th.rand(2, 2, 3, 16, 16, generator=g),
+             "features": th.randn(2, 2, 6, 16, 16, generator=g),
+             "global_features": th.randn(2, 2, 1, 1, generator=g),
+             "target_image": th.rand(2, 3, 16, 16, generator=g)}
+    steps = []
+    for _ in range(2):
+        b = {k_: v.clone() for k_, v in batch.items()}
+        steps.append(iface.backward(b, iface.forward(b)))
+    out["train_steps"] = {"ctor": dict(n_features=6, n_global_features=2, width=8,
+                                       embedding_width=8, ksize=3, nsteps=1),
+                          "init": init, "batch": batch, "steps": steps, "lr": 1e-3,
+                          "final": {k_: v.clone() for k_, v in net.state_dict().items()}}
 
     path = os.path.join(HERE, "model_golden.pt")
     th.save(out, path)

@@ -108,6 +108,23 @@ def test_kpcn_matches_reference_run(golden, oracle_ops):
     _check_kpcn(golden, "cpu", 1e-5, 1e-6)
 
 
+def test_training_steps_match_reference_run(golden, oracle_ops):
+    """Two Adam steps through the reference's SampleBasedDenoiserInterface
+    (sbmc/interfaces.py:62-106: loss, clip, Adam, rmse) reproduced by ours."""
+    from sbmc_b200 import interfaces
+    case = golden["train_steps"]
+    net = models.Multisteps(**case["ctor"])
+    net.load_state_dict(case["init"], strict=True)
+    iface = interfaces.SampleBasedDenoiserInterface(net, lr=case["lr"], cuda=False)
+    for want in case["steps"]:
+        b = {k: v.clone() for k, v in case["batch"].items()}
+        got = iface.backward(b, iface.forward(b))
+        assert abs(got["loss"] - want["loss"]) <= 1e-6 * abs(want["loss"]) + 1e-9
+        assert abs(got["rmse"] - want["rmse"]) <= 1e-6 * abs(want["rmse"]) + 1e-9
+    for name, want in case["final"].items():
+        _close(net.state_dict()[name], want, 1e-5, 1e-7)
+
+
 @pytest.fixture
 def fp32_convs(monkeypatch):
     monkeypatch.setattr(th.backends.cudnn, "allow_tf32", False)

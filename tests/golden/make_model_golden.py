@@ -161,6 +161,12 @@ def main():
                           "init": init, "batch": batch, "steps": steps, "lr": 1e-3,
                           "final": {k_: v.clone() for k_, v in net.state_dict().items()}}
 
+    # -- parameter names / shapes of the full-size models (checkpoint compatibility) ---
+    full = ref["models"].Multisteps(93, 3)
+    out["multisteps_93_3_keys"] = {k_: tuple(v.shape) for k_, v in full.state_dict().items()}
+    full = ref["models"].KPCN(27)
+    out["kpcn_27_keys"] = {k_: tuple(v.shape) for k_, v in full.state_dict().items()}
+
     path = os.path.join(HERE, "model_golden.pt")
     th.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -108,6 +108,15 @@ def test_kpcn_matches_reference_run(golden, oracle_ops):
     _check_kpcn(golden, "cpu", 1e-5, 1e-6)
 
 
+def test_full_size_state_dict_names_match_reference(golden):
+    """Same parameter names and shapes as the reference's Multisteps(93, 3) / KPCN(27)
+    (so that the published checkpoints, Makefile:213, load with strict=True)."""
+    mine = {k: tuple(v.shape) for k, v in models.Multisteps(93, 3).state_dict().items()}
+    assert mine == golden["multisteps_93_3_keys"]
+    mine = {k: tuple(v.shape) for k, v in models.KPCN(27).state_dict().items()}
+    assert mine == golden["kpcn_27_keys"]
+
+
 def test_training_steps_match_reference_run(golden, oracle_ops):
     """Two Adam steps through the reference's SampleBasedDenoiserInterface
     (sbmc/interfaces.py:62-106: loss, clip, Adam, rmse) reproduced by ours."""

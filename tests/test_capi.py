@@ -59,6 +59,31 @@ def test_argument_validation_needs_no_gpu():
         _lib.check(rc, "kernel_weighting")
 
 
+def test_plain_c_client_builds_links_and_validates(tmp_path):
+    """include/sbmc_b200.h is a C header: a C99 client compiles with -pedantic,
+    links every declared entry point and gets the documented status codes."""
+    import shutil
+    import subprocess
+    _lib.load()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cabi_client.c")
+    text = open(src).read()
+    for name in declared_symbols():
+        assert name in text, "cabi_client.c does not reference " + name
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                           "-I", os.path.join(root, "include"), src,
+                           "-o", exe, "-L", libdir, "-l:libsbmc_b200.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "failures: 0" in out.stdout
+
+
 def test_drop_in_module_has_the_reference_names():
     # reference setup.py:65-84
     for op in ("scatter2gather", "kernel_weighting", "kernel_weighting_grad"):

@@ -86,7 +86,8 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_SPLAT_FWD 5    /* fused ProgressiveKernelApply forward   */
 #define SBMC_KERNEL_SPLAT_BWD 6    /* fused ProgressiveKernelApply backward  */
 #define SBMC_KERNEL_CONV1X1 7      /* fused 3-layer 1x1 ConvChain (tcgen05)  */
-#define SBMC_NUM_KERNEL_KINDS 8
+#define SBMC_KERNEL_TILES 8        /* tile reader: LZ4 inflate + assembly    */
+#define SBMC_NUM_KERNEL_KINDS 9
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
 
@@ -201,6 +202,63 @@ SBMC_API int sbmc_bias_act_nhwc_bf16(void *y, const float *bias, int64_t pixels,
 SBMC_API int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void *y,
                            int64_t y_img_stride, int64_t n, int c, int64_t hw, int cpad,
                            void *stream);
+
+/* ---- sample-buffer reader (the callers' input format, sbmc/datasets.py) --- *
+ * A .bin tile is a header followed by 1 + sample_count chunks, each an int32
+ * byte count and an LZ4 frame (writer: pbrt_patches/sbmc_pbrt.diff:6140-6158).
+ * The host parses the header and the chunk sizes (sbmc_b200/datasets.py), ships
+ * the COMPRESSED bytes to the device, and these two entry points replace
+ * `lz4.frame.decompress` (datasets.py:570-579) and the numpy assembly of
+ * `TilesDataset._read_data` / `_preprocess_standard` /
+ * `FullImagesDataset.__getitem__` (datasets.py:581-739, 744-778, 920-957). */
+
+/* Inflates `nframes` LZ4 frames on the device, one warp per frame.
+ * frame_table (device) is int64 [nframes][4] = {source byte offset in src,
+ * source byte count, destination byte offset in dst, expected inflated size};
+ * status (device, int32 [nframes]) receives 0 or an SBMC_LZ4_* code per frame
+ * (the call itself only fails for bad arguments / launch errors).  Frame and
+ * block checksums are skipped, not verified. */
+#define SBMC_LZ4_OK 0
+#define SBMC_LZ4_BAD_MAGIC 1
+#define SBMC_LZ4_BAD_HEADER 2
+#define SBMC_LZ4_TRUNCATED 3
+#define SBMC_LZ4_OVERFLOW 4
+#define SBMC_LZ4_BAD_OFFSET 5
+#define SBMC_LZ4_SIZE_MISMATCH 6
+#define SBMC_LZ4_BLOCK_TOO_LARGE 7
+SBMC_API int sbmc_lz4_frames_inflate(const void *src, const int64_t *frame_table,
+                                     int64_t nframes, void *dst, int32_t *status,
+                                     void *stream);
+
+/* Builds the model's input tensors from inflated tiles.  raw (device) holds,
+ * per tile, one image frame ([pixel_features][ts][ts] fp32: channel means then
+ * variances) and spp sample frames `sample_stride_bytes` apart ([27 + 6*depth]
+ * fp32 planes then [depth] int16 bounce-type planes, each [ts][ts]);
+ * tile_table (device) is int64 [ntiles][4] = {image frame byte offset, first
+ * sample frame byte offset, block_x, block_y}.  Outputs are planar fp32, the
+ * tile pasted at rows block_y.., columns block_x.. of an h x w image:
+ *   features [spp][nf][h][w]   (channel selection by SBMC_TILE_* flags, bounce
+ *                               types expanded to 5 flag planes per vertex;
+ *                               SBMC_TILE_LOG_RADIANCE applies the sbmc-mode
+ *                               log(1 + max(.,0)) / 10 compression in place)
+ *   radiance [spp][3][h][w]    diffuse + specular, raw
+ *   low_spp  [3][h][w]         mean of radiance over the samples
+ *   image_data / image_data_var [pixel_features/2][h][w], target_image [3][h][w]
+ * Pixels no tile covers are left untouched (zero them first).  spp == 0 or
+ * pixel_features == 0 skips the corresponding outputs (pointers may be NULL). */
+#define SBMC_TILE_COORDS 1
+#define SBMC_TILE_GBUFFER 2
+#define SBMC_TILE_P 4
+#define SBMC_TILE_LD 8
+#define SBMC_TILE_BT 16
+#define SBMC_TILE_LOG_RADIANCE 32
+#define SBMC_TILE_ALIGNED 64   /* frame offsets % 16 == 0 and block_x % 4 == 0 */
+SBMC_API int sbmc_tile_assemble_f32(const void *raw, const int64_t *tile_table, int64_t ntiles,
+                                    int64_t sample_stride_bytes, int ts, int spp,
+                                    int sample_features, int pixel_features, int path_depth,
+                                    int flags, float *features, float *radiance,
+                                    float *low_spp, float *image_data, float *image_data_var,
+                                    float *target_image, int64_t h, int64_t w, void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

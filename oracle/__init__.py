@@ -36,7 +36,8 @@ def _cpu_signature():
                     break
     except OSError:
         pass
-    src = open(os.path.join(_HERE, "sbmc_oracle.c"), "rb").read()
+    src = b"".join(open(os.path.join(_HERE, f), "rb").read()
+                   for f in ("sbmc_oracle.c", "lz4_oracle.c", "Makefile"))
     return hashlib.sha1(flags.encode() + src).hexdigest()
 
 
@@ -71,6 +72,10 @@ def lib():
                   L.sbmc_oracle_scatter2gather_f32,
                   L.sbmc_oracle_num_threads):
             f.restype = i32
+        L.sbmc_oracle_lz4_frame_decompress.argtypes = [fp, i64, fp, i64, fp]
+        L.sbmc_oracle_lz4_frame_decompress.restype = i32
+        L.sbmc_oracle_xxh32.argtypes = [fp, i64, ctypes.c_uint32]
+        L.sbmc_oracle_xxh32.restype = ctypes.c_uint32
         _lib = L
     return _lib
 
@@ -159,3 +164,37 @@ def scatter2gather(weights):
     out = th.empty_like(weights)
     scatter2gather_cpu_float32(weights, out)
     return out
+
+
+# -- the tile reader's decompressor (reference: lz4.frame.decompress) ---------------
+class Lz4Error(RuntimeError):
+    def __init__(self, code):
+        RuntimeError.__init__(self, "lz4 frame decode failed with code %d" % code)
+        self.code = code
+
+
+def lz4_frame_decompress(buf, max_size=None):
+    """bytes -> bytes, like `lz4.frame.decompress` (sbmc/datasets.py:578).  The
+    output buffer grows until the frame fits (the format does not have to carry
+    its content size)."""
+    buf = bytes(buf)
+    cap = max(4 * len(buf), 1 << 16) if max_size is None else int(max_size)
+    src = ctypes.create_string_buffer(buf, len(buf))
+    while True:
+        dst = ctypes.create_string_buffer(cap)
+        out_len = ctypes.c_int64(0)
+        rc = lib().sbmc_oracle_lz4_frame_decompress(
+            ctypes.cast(src, ctypes.c_void_p), len(buf), ctypes.cast(dst, ctypes.c_void_p),
+            cap, ctypes.cast(ctypes.pointer(out_len), ctypes.c_void_p))
+        if rc == 4 and max_size is None and cap < (1 << 34):   # overflow: retry larger
+            cap *= 4
+            continue
+        if rc != 0:
+            raise Lz4Error(rc)
+        return dst.raw[:out_len.value]
+
+
+def xxh32(buf, seed=0):
+    buf = bytes(buf)
+    src = ctypes.create_string_buffer(buf, len(buf))
+    return int(lib().sbmc_oracle_xxh32(ctypes.cast(src, ctypes.c_void_p), len(buf), seed))

@@ -43,6 +43,10 @@ SIGNATURES = {
         (_int, [_ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_bias_act_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _ptr]),
     "sbmc_nchw_to_nhwc_bf16": (_int, [_ptr, _i64, _ptr, _i64, _i64, _int, _i64, _int, _ptr]),
+    "sbmc_lz4_frames_inflate": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "sbmc_tile_assemble_f32":
+        (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _ptr,
+                _ptr, _ptr, _ptr, _i64, _i64, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
@@ -111,8 +115,8 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain"}
-NUM_KERNEL_KINDS = 8
+                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain", 8: "tiles"}
+NUM_KERNEL_KINDS = 9
 
 
 def timing_enable(flag):

@@ -1,0 +1,214 @@
+// lz4_warp.cuh -- LZ4 *frame* inflater, one warp per frame.
+//
+// The reference stores every tile as a header plus (1 + sample_count) LZ4
+// frames (writer: LZ4F_compressFrame with default preferences,
+// pbrt_patches/sbmc_pbrt.diff:6140-6158; reader: lz4.frame.decompress,
+// sbmc/datasets.py:570-579).  lz4 itself is a third-party dependency that is
+// not vendored (setup.py:104 `lz4`, liblz4-dev in dockerfiles/*.dockerfile);
+// this file restates its published formats:
+//   frame  = magic 0x184D2204, FLG, BD, [content size 8B], [dict id 4B], HC,
+//            blocks { u32 size (bit 31 = stored raw), data, [u32 checksum] },
+//            end mark 0, [u32 content checksum]
+//   block  = sequences { token, literal-length bytes, literals,
+//            u16 offset, match-length bytes }, the last sequence stops after
+//            its literals.  Blocks of one frame may reference up to 64 KiB of
+//            earlier output of the same frame ("linked" blocks, the default).
+//
+// Parallel form: the control state (read / write cursors, lengths) is
+// warp-uniform -- every lane parses the same token bytes (one broadcast load)
+// -- and only the two copy loops are split over the lanes.  A match that
+// overlaps its own output (offset < length) is periodic with period `offset`,
+// so lane i reads dst[op - offset + i % offset]: every read lies below `op`,
+// i.e. in bytes finished before this sequence, and no intra-sequence ordering
+// is needed.  One __syncwarp() per sequence publishes the bytes to the lanes
+// that read them next.
+//
+// The same source compiles for the host (tests/lz4_emul.cpp) with the lane
+// loops run sequentially, so the cursor arithmetic is checked on CPU against
+// the reference library's own output; checksums are skipped, not verified.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__)
+#define SBMC_LZ4_FN __device__ __forceinline__
+#define SBMC_LZ4_LANES(lane) for (int lane = (int)(threadIdx.x & 31u), once__ = 1; once__; once__ = 0)
+#define SBMC_LZ4_PUBLISH() __syncwarp()
+#else
+#define SBMC_LZ4_FN static inline
+#define SBMC_LZ4_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define SBMC_LZ4_PUBLISH() ((void)0)
+#endif
+
+namespace sbmc {
+namespace lz4 {
+
+enum Status : int {
+  kOk = 0,
+  kBadMagic = 1,      // not an LZ4 frame
+  kBadHeader = 2,     // unsupported version / reserved bits / block size id
+  kTruncated = 3,     // input ends inside a header, block or sequence
+  kOverflow = 4,      // output would exceed the caller's capacity
+  kBadOffset = 5,     // match offset 0 or beyond the produced output
+  kSizeMismatch = 6,  // decoded size differs from the size the tile header implies
+  kBlockTooLarge = 7, // block larger than the frame's declared maximum
+};
+
+SBMC_LZ4_FN uint32_t load_u32(const uint8_t *p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// Copies n bytes src -> dst, lanes interleaved byte-wise (32 consecutive bytes
+// per warp access = one sector), four accesses in flight per lane.
+SBMC_LZ4_FN void copy_lanes(uint8_t *dst, const uint8_t *src, int64_t n) {
+  SBMC_LZ4_LANES(lane) {
+    int64_t i = lane;
+    for (; i + 96 < n; i += 128) {
+      uint8_t a = src[i], b = src[i + 32], c = src[i + 64], d = src[i + 96];
+      dst[i] = a;
+      dst[i + 32] = b;
+      dst[i + 64] = c;
+      dst[i + 96] = d;
+    }
+    for (; i < n; i += 32) dst[i] = src[i];
+  }
+}
+
+// dst[0..n) = the `offset` bytes before dst, repeated.  Reads stay below dst.
+SBMC_LZ4_FN void match_lanes(uint8_t *dst, int64_t offset, int64_t n) {
+  const uint8_t *from = dst - offset;
+  if (offset >= n) {
+    copy_lanes(dst, from, n);
+    return;
+  }
+  SBMC_LZ4_LANES(lane) {
+    // i % offset without a division per byte: advance a running remainder.
+    int64_t i = lane;
+    int64_t r = lane % offset;
+    const int64_t step = 32 % offset;
+    for (; i < n; i += 32) {
+      dst[i] = from[r];
+      r += step;
+      if (r >= offset) r -= offset;
+    }
+  }
+}
+
+// One LZ4 block [ip, ip_end) appended at dst + op; `window` = first output byte
+// a match may reference.  Returns a Status; *op_io advances by the block's size.
+SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *dst,
+                             int64_t *op_io, int64_t dst_cap, int64_t window) {
+  int64_t op = *op_io;
+  for (;;) {
+    if (ip >= ip_end) return kTruncated;
+    const uint32_t token = *ip++;
+    int64_t lit = token >> 4;
+    if (lit == 15) {
+      uint32_t b;
+      do {
+        if (ip >= ip_end) return kTruncated;
+        b = *ip++;
+        lit += b;
+      } while (b == 255);
+    }
+    if (lit > ip_end - ip) return kTruncated;
+    if (lit > dst_cap - op) return kOverflow;
+    copy_lanes(dst + op, ip, lit);
+    ip += lit;
+    op += lit;
+    if (ip == ip_end) break;  // the last sequence carries literals only
+    if (ip_end - ip < 2) return kTruncated;
+    const int64_t offset = (int64_t)ip[0] | ((int64_t)ip[1] << 8);
+    ip += 2;
+    int64_t mlen = token & 15;
+    if (mlen == 15) {
+      uint32_t b;
+      do {
+        if (ip >= ip_end) return kTruncated;
+        b = *ip++;
+        mlen += b;
+      } while (b == 255);
+    }
+    mlen += 4;
+    if (offset == 0 || offset > op - window) return kBadOffset;
+    if (mlen > dst_cap - op) return kOverflow;
+    SBMC_LZ4_PUBLISH();  // the literals just written may be the match source
+    match_lanes(dst + op, offset, mlen);
+    op += mlen;
+    SBMC_LZ4_PUBLISH();
+  }
+  SBMC_LZ4_PUBLISH();
+  *op_io = op;
+  return kOk;
+}
+
+// Inflates src[0..src_len) (one or more concatenated frames, skippable frames
+// ignored) into dst[0..dst_cap).  *out_len = bytes produced.  Warp-uniform.
+SBMC_LZ4_FN int decode_frames(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_cap,
+                              int64_t *out_len) {
+  const uint8_t *ip = src;
+  const uint8_t *const end = src + src_len;
+  int64_t op = 0;
+  int frames = 0;
+  *out_len = 0;
+  while (ip < end) {
+    if (end - ip < 4) return kTruncated;
+    const uint32_t magic = load_u32(ip);
+    ip += 4;
+    if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+      if (end - ip < 4) return kTruncated;
+      const int64_t skip = load_u32(ip);
+      ip += 4;
+      if (skip > end - ip) return kTruncated;
+      ip += skip;
+      continue;
+    }
+    if (magic != 0x184D2204u) return frames ? kOk : kBadMagic;  // trailing bytes: ignored
+    if (end - ip < 3) return kTruncated;
+    const uint32_t flg = ip[0], bd = ip[1];
+    ip += 2;
+    if ((flg >> 6) != 1 || (flg & 2) || (bd & 0x8F)) return kBadHeader;
+    const bool independent = flg & 0x20, block_sum = flg & 0x10, has_size = flg & 8,
+               content_sum = flg & 4, has_dict = flg & 1;
+    const int size_id = (bd >> 4) & 7;
+    if (size_id < 4) return kBadHeader;
+    const int64_t block_max = (int64_t)1 << (8 + 2 * size_id);
+    const int64_t skip = (has_size ? 8 : 0) + (has_dict ? 4 : 0) + 1;  // + header checksum
+    if (skip > end - ip) return kTruncated;
+    ip += skip;
+    const int64_t frame_start = op;
+    for (;;) {
+      if (end - ip < 4) return kTruncated;
+      const uint32_t word = load_u32(ip);
+      ip += 4;
+      if (word == 0) break;  // end mark
+      const int64_t bsize = word & 0x7FFFFFFFu;
+      if (bsize > block_max) return kBlockTooLarge;
+      if (bsize > end - ip) return kTruncated;
+      if (word & 0x80000000u) {  // stored block
+        if (bsize > dst_cap - op) return kOverflow;
+        copy_lanes(dst + op, ip, bsize);
+        op += bsize;
+        SBMC_LZ4_PUBLISH();
+      } else {
+        const int rc = decode_block(ip, ip + bsize, dst, &op, dst_cap, independent ? op : frame_start);
+        if (rc != kOk) return rc;
+      }
+      ip += bsize;
+      if (block_sum) {
+        if (end - ip < 4) return kTruncated;
+        ip += 4;
+      }
+    }
+    if (content_sum) {
+      if (end - ip < 4) return kTruncated;
+      ip += 4;
+    }
+    ++frames;
+    *out_len = op;
+  }
+  *out_len = op;
+  return frames ? kOk : kBadMagic;
+}
+
+}  // namespace lz4
+}  // namespace sbmc

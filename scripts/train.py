@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Train a denoiser: the caller of the hot path at training time.  Same options
+and flow as the reference's scripts/train.py (:32-152): TilesDataset /
+MultiSampleCountDataset -> Multisteps / KPCN -> SampleBasedDenoiserInterface
+(Adam, tonemapped relative MSE, gradient clipping) -> checkpoints whose meta holds
+model_params / kpcn_mode / data_params for scripts/denoise.py.
+
+The `ttools` trainer, argument parser and callbacks are external to the reference
+tree and absent here; sbmc_b200._compat carries small equivalents (no Visdom
+display).  Samples are inflated and assembled on the GPU, so the DataLoader runs
+without worker processes.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch as th
+from torch.utils.data import DataLoader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from sbmc_b200 import _compat, datasets, interfaces, models  # noqa: E402
+
+LOG = _compat.get_logger(__name__)
+
+
+def main(args):
+    np.random.seed(0)
+    th.manual_seed(0)
+    if not th.cuda.is_available():
+        raise RuntimeError("sbmc_b200 runs on a CUDA device only (no CPU path)")
+    data_args = dict(spp=args.spp,
+                     mode=datasets.TilesDataset.KPCN_MODE if args.kpcn_mode
+                     else datasets.TilesDataset.SBMC_MODE,
+                     load_coords=args.load_coords, load_gbuffer=args.load_gbuffer,
+                     load_p=args.load_p, load_ld=args.load_ld, load_bt=args.load_bt)
+    if args.randomize_spp:
+        if args.bs != 1:
+            LOG.error("Training with randomized spp is only valid for batch_size=1, got %d",
+                      args.bs)
+            raise RuntimeError("Incorrect batch size")
+        data = datasets.MultiSampleCountDataset(args.data, **data_args)
+        LOG.info("Training with randomized sample count in [%d, %d]", 2, args.spp)
+    else:
+        data = datasets.TilesDataset(args.data, **data_args)
+        LOG.info("Training with a single sample count: %dspp", args.spp)
+
+    if args.kpcn_mode:
+        model = models.KPCN(data.num_features, ksize=args.ksize)
+        model_params = dict(ksize=args.ksize)
+    else:
+        model = models.Multisteps(data.num_features, data.num_global_features, ksize=args.ksize,
+                                  splat=not args.gather, pixel=args.pixel)
+        model_params = dict(ksize=args.ksize, gather=args.gather, pixel=args.pixel)
+
+    loader = DataLoader(data, batch_size=args.bs, num_workers=0, shuffle=True)
+    val_loader = None
+    if args.val_data is not None:
+        val = datasets.TilesDataset(args.val_data, **data_args)
+        val_loader = DataLoader(val, batch_size=args.bs, num_workers=0, shuffle=False)
+
+    meta = dict(model_params=model_params, kpcn_mode=args.kpcn_mode, data_params=data_args)
+    LOG.info("Model configuration: %s", model_params)
+    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=True)
+    checkpointer = _compat.Checkpointer(args.checkpoint_dir, model, meta=meta,
+                                        optimizers=interface.optimizer)
+    checkpointer.load_latest()
+
+    trainer = _compat.Trainer(interface)
+    trainer.add_callback(_compat.LoggingCallback(["loss", "rmse"], frequency=args.log_every))
+    trainer.add_callback(_compat.CheckpointingCallback(checkpointer))
+    LOG.info("Training started, 'Ctrl+C' to abort.")
+    trainer.train(loader, num_epochs=args.num_epochs, val_dataloader=val_loader,
+                  max_steps=args.max_steps)
+
+
+def parser():
+    p = argparse.ArgumentParser()
+    # ttools.BasicArgumentParser's options used by the reference script
+    p.add_argument("--data", required=True, help="path to the training data.")
+    p.add_argument("--val_data", help="path to the validation data.")
+    p.add_argument("--checkpoint_dir", required=True, help="output directory.")
+    p.add_argument("--lr", type=float, default=1e-4)
+    p.add_argument("--bs", type=int, default=1)
+    p.add_argument("--num_epochs", type=int)
+    p.add_argument("--max_steps", type=int, help="stop after this many steps (extra).")
+    p.add_argument("--log_every", type=int, default=50)
+    p.add_argument("--spp", type=int, default=8, help="Max number of samples per pixel.")
+    p.add_argument("--kpcn_mode", dest="kpcn_mode", action="store_true", default=False)
+    p.add_argument("--gather", dest="gather", action="store_true", default=False)
+    p.add_argument("--pixel", dest="pixel", action="store_true", default=False)
+    p.add_argument("--ksize", type=int, default=21, help="Size of the kernels")
+    p.add_argument("--constant_spp", dest="randomize_spp", action="store_false", default=True)
+    p.add_argument("--dont_use_coords", dest="load_coords", action="store_false", default=True)
+    p.add_argument("--dont_use_gbuffer", dest="load_gbuffer", action="store_false", default=True)
+    p.add_argument("--dont_use_p", dest="load_p", action="store_false", default=True)
+    p.add_argument("--dont_use_ld", dest="load_ld", action="store_false", default=True)
+    p.add_argument("--dont_use_bt", dest="load_bt", action="store_false", default=True)
+    return p
+
+
+if __name__ == "__main__":
+    main(parser().parse_args())

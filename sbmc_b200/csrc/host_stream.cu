@@ -144,6 +144,32 @@ static int copy_planes_d2h(float *dst, const float *src, i64 rows_w, i64 dst_pla
   return SBMC_OK;
 }
 
+// The host entry points select `device` for their own work and give the caller
+// its current device back on return.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// After a failure half-way through a pipeline: copies already queued still
+// read / write the caller's host buffers, so wait for them before returning
+// (keeps the error message of the call that failed).
+static int drain_on_error(HostPipe &P, int rc) {
+  if (rc != SBMC_OK) {
+    if (P.s_h2d) cudaStreamSynchronize(P.s_h2d);
+    if (P.s_comp) cudaStreamSynchronize(P.s_comp);
+    if (P.s_d2h) cudaStreamSynchronize(P.s_d2h);
+  }
+  return rc;
+}
+
 static int sync_all(HostPipe &P) {
   SBMC_CUDA_OK(cudaStreamSynchronize(P.s_h2d));
   SBMC_CUDA_OK(cudaStreamSynchronize(P.s_comp));
@@ -151,12 +177,10 @@ static int sync_all(HostPipe &P) {
   return SBMC_OK;
 }
 
-static int fwd_host(const float *data, const float *weights, float *output,
+static int fwd_host_locked(const float *data, const float *weights, float *output,
                     float *sum_w, i64 n, int c, i64 h, i64 w, int kh, int kw,
                     int device) {
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  int rc = pipe_init_locked(device);
-  if (rc) return rc;
+  int rc = SBMC_OK;
   HostPipe &P = g_pipe;
   const i64 taps = (i64)kh * kw, plane = h * w;
   const i64 hb = band_rows(h, w, taps);
@@ -204,12 +228,10 @@ static int fwd_host(const float *data, const float *weights, float *output,
   return sync_all(P);
 }
 
-static int bwd_host(const float *data, const float *weights, const float *d_output,
+static int bwd_host_locked(const float *data, const float *weights, const float *d_output,
                     const float *d_sum_w, float *d_data, float *d_weights, i64 n,
                     int c, i64 h, i64 w, int kh, int kw, int device) {
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  int rc = pipe_init_locked(device);
-  if (rc) return rc;
+  int rc = SBMC_OK;
   HostPipe &P = g_pipe;
   const i64 taps = (i64)kh * kw, plane = h * w;
   const i64 hb = band_rows(h, w, taps);
@@ -289,13 +311,11 @@ static int bwd_host(const float *data, const float *weights, const float *d_outp
   return sync_all(P);
 }
 
-static int s2g_host(const float *scatter, float *gather, i64 n, int kh, int kw,
+static int s2g_host_locked(const float *scatter, float *gather, i64 n, int kh, int kw,
                     i64 h, i64 w, int device) {
   // The transpose mixes rows of different taps, so bands do not help: stream one
   // image (all taps) at a time through two device buffers.
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  int rc = pipe_init_locked(device);
-  if (rc) return rc;
+  int rc = SBMC_OK;
   HostPipe &P = g_pipe;
   const i64 img_elems = (i64)kh * kw * h * w;
   float *g_in[2], *g_out[2];
@@ -325,6 +345,37 @@ static int s2g_host(const float *scatter, float *gather, i64 n, int kh, int kw,
   return sync_all(P);
 }
 
+// Public bodies: serialise on the pipe, select the device, drain on failure.
+template <typename Fn>
+static int with_pipe(int device, Fn body) {
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  DeviceGuard guard;
+  int rc = pipe_init_locked(device);
+  if (rc) return rc;
+  return drain_on_error(g_pipe, body());
+}
+
+static int fwd_host(const float *data, const float *weights, float *output, float *sum_w, i64 n,
+                    int c, i64 h, i64 w, int kh, int kw, int device) {
+  return with_pipe(device, [&] {
+    return fwd_host_locked(data, weights, output, sum_w, n, c, h, w, kh, kw, device);
+  });
+}
+
+static int bwd_host(const float *data, const float *weights, const float *d_output,
+                    const float *d_sum_w, float *d_data, float *d_weights, i64 n, int c, i64 h,
+                    i64 w, int kh, int kw, int device) {
+  return with_pipe(device, [&] {
+    return bwd_host_locked(data, weights, d_output, d_sum_w, d_data, d_weights, n, c, h, w, kh,
+                           kw, device);
+  });
+}
+
+static int s2g_host(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h, i64 w,
+                    int device) {
+  return with_pipe(device, [&] { return s2g_host_locked(scatter, gather, n, kh, kw, h, w, device); });
+}
+
 static int check_host_args(i64 n, int c, i64 h, i64 w, int kh, int kw,
                            const void *const *ptrs, int count) {
   if (n < 0 || h < 0 || w < 0 || c < 1 || kh < 1 || kw < 1) {
@@ -347,6 +398,7 @@ extern "C" {
 
 int sbmc_b200_host_release(void) {
   std::lock_guard<std::mutex> lock(sbmc::g_pipe_mu);
+  sbmc::DeviceGuard guard;
   return sbmc::pipe_release_locked();
 }
 

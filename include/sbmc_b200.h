@@ -245,7 +245,10 @@ SBMC_API int sbmc_lz4_frames_inflate(const void *src, const int64_t *frame_table
  *   low_spp  [3][h][w]         mean of radiance over the samples
  *   image_data / image_data_var [pixel_features/2][h][w], target_image [3][h][w]
  * Pixels no tile covers are left untouched (zero them first).  spp == 0 or
- * pixel_features == 0 skips the corresponding outputs (pointers may be NULL). */
+ * pixel_features == 0 skips the corresponding outputs (pointers may be NULL).
+ * `row0` is the image row the outputs start at: they hold rows row0 .. row0+h-1
+ * and tile rows outside that range are skipped, so a rank of a row-sharded job
+ * assembles just its band (0 and h = image height for the whole image). */
 #define SBMC_TILE_COORDS 1
 #define SBMC_TILE_GBUFFER 2
 #define SBMC_TILE_P 4
@@ -258,7 +261,8 @@ SBMC_API int sbmc_tile_assemble_f32(const void *raw, const int64_t *tile_table, 
                                     int sample_features, int pixel_features, int path_depth,
                                     int flags, float *features, float *radiance,
                                     float *low_spp, float *image_data, float *image_data_var,
-                                    float *target_image, int64_t h, int64_t w, void *stream);
+                                    float *target_image, int64_t h, int64_t w, int64_t row0,
+                                    void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

@@ -46,7 +46,7 @@ SIGNATURES = {
     "sbmc_lz4_frames_inflate": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "sbmc_tile_assemble_f32":
         (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _ptr,
-                _ptr, _ptr, _ptr, _i64, _i64, _ptr]),
+                _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),

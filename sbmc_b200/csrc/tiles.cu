@@ -28,11 +28,9 @@ __global__ void __launch_bounds__(32) lz4_frames_kernel(const uint8_t *__restric
   if (f >= nframes) return;
   const i64 src_off = table[4 * f + 0], src_len = table[4 * f + 1];
   const i64 dst_off = table[4 * f + 2], dst_len = table[4 * f + 3];
-  long long produced = 0;
   int64_t out_len = 0;
   int rc = lz4::decode_frames(src + src_off, src_len, dst + dst_off, dst_len, &out_len);
-  produced = out_len;
-  if (rc == lz4::kOk && produced != dst_len) rc = lz4::kSizeMismatch;
+  if (rc == lz4::kOk && out_len != dst_len) rc = lz4::kSizeMismatch;
   if ((threadIdx.x & 31) == 0) status[f] = rc;
 }
 
@@ -88,12 +86,12 @@ int sbmc_tile_assemble_f32(const void *raw, const int64_t *tile_table, int64_t n
                            int pixel_features, int path_depth, int flags, float *features,
                            float *radiance, float *low_spp, float *image_data,
                            float *image_data_var, float *target_image, int64_t h, int64_t w,
-                           void *stream) {
+                           int64_t row0, void *stream) {
   sbmc::TileAssembleParams p;
   int rc = sbmc::tile_assemble_params(&p, raw, tile_table, ntiles, sample_stride_bytes, ts, spp,
                                       sample_features, pixel_features, path_depth, flags, features,
                                       radiance, low_spp, image_data, image_data_var, target_image,
-                                      h, w);
+                                      h, w, row0);
   if (rc == 1) return SBMC_OK;  // nothing to do
   if (rc < 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -29,7 +29,7 @@ void set_error(const char *fmt, ...);
 struct TileAssembleParams {
   const uint8_t *raw;
   const long long *tiles;  // [ntiles][4]: image frame offset, first sample frame offset, block_x, block_y
-  long long ntiles, sample_stride, h, w;
+  long long ntiles, sample_stride, h, w, row0;
   int ts, spp, nf, nchans, pixel_features, depth;
   int float_planes;         // fp32 planes in a sample frame (sample_features + 6*depth)
   int i_diffuse;            // output channel of diffuse_r (specular_r = +3)
@@ -46,8 +46,9 @@ static inline int tile_assemble_params(TileAssembleParams *p, const void *raw,
                                        int sample_features, int pixel_features, int path_depth,
                                        int flags, float *features, float *radiance, float *low_spp,
                                        float *image_data, float *image_data_var,
-                                       float *target_image, int64_t h, int64_t w) {
-  if (ntiles < 0 || ts < 1 || spp < 0 || h < ts || w < ts || path_depth < 0 || pixel_features < 0) {
+                                       float *target_image, int64_t h, int64_t w,
+                                       int64_t row0) {
+  if (ntiles < 0 || ts < 1 || spp < 0 || h < 1 || w < ts || path_depth < 0 || pixel_features < 0) {
     set_error("tile assembly: invalid shape ntiles=%lld ts=%d spp=%d h=%lld w=%lld depth=%d",
               (long long)ntiles, ts, spp, (long long)h, (long long)w, path_depth);
     return SBMC_EINVAL;
@@ -110,6 +111,7 @@ static inline int tile_assemble_params(TileAssembleParams *p, const void *raw,
   p->sample_stride = sample_stride_bytes;
   p->h = h;
   p->w = w;
+  p->row0 = row0;
   p->ts = ts;
   p->spp = spp;
   p->nf = nf;
@@ -186,7 +188,9 @@ SBMC_HD void tile_assemble_body(const TileAssembleParams &p, long long tile, int
   const long long plane_in = (long long)p.ts * p.ts;     // elements
   const long long plane_out = p.h * p.w;                 // elements
   const long long in_px = (long long)y * p.ts + x;
-  const long long out_px = (by + y) * p.w + bx + x;
+  const long long oy = by + y - p.row0;                  // row in the (band of the) output
+  if (oy < 0 || oy >= p.h) return;
+  const long long out_px = oy * p.w + bx + x;
 
   // ---- pixel statistics (datasets.py:592-606) --------------------------------
   if (p.pixel_features > 0) {

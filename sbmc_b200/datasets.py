@@ -320,9 +320,10 @@ class TilesDataset(Dataset):
             src += _align(pos, 16)      # chunks past `spp` are not shipped: overwritten next
         return stage[:max(src, 1)], frames, tiles, dst
 
-    def _read_tiles(self, fnames, height, width, positions=None):
+    def _read_tiles(self, fnames, height, width, positions=None, row0=0):
         """Inflates and assembles `fnames` into one set of [.., height, width]
-        tensors; `positions` overrides the tiles' (block_x, block_y)."""
+        tensors holding image rows row0 .. row0 + height - 1 (tile rows outside are
+        skipped); `positions` overrides the tiles' (block_x, block_y)."""
         dev = self._device()
         lib = _lib.load()
         stage, frames, tiles, raw_bytes = self._plan(fnames)
@@ -342,7 +343,7 @@ class TilesDataset(Dataset):
             aligned = True
             for i, t in enumerate(tiles):
                 bx, by = positions[i] if positions is not None else (t["block_x"], t["block_y"])
-                if bx < 0 or by < 0 or bx + ts > width or by + ts > height:
+                if bx < 0 or by < 0 or bx + ts > width or (row0 == 0 and by + ts > height):
                     raise ValueError("tile %s at (%d, %d) does not fit a %dx%d image"
                                      % (t["path"], bx, by, width, height))
                 aligned &= bx % 4 == 0
@@ -363,7 +364,8 @@ class TilesDataset(Dataset):
                 ts, spp, self.sample_features, self.pixel_features, self.path_depth,
                 self._flags() | (_F_ALIGNED if aligned else 0), ptr("features"), ptr("radiance"),
                 ptr("low_spp"), out["image_data"].data_ptr(), out["image_data_var"].data_ptr(),
-                out["target_image"].data_ptr(), height, width, stream.cuda_stream), "tile_assemble")
+                out["target_image"].data_ptr(), height, width, row0, stream.cuda_stream),
+                "tile_assemble")
             bad = status.cpu()      # also orders the staging buffer's reuse after the copy
         if bool(bad.any()):
             f = int(bad.nonzero()[0])
@@ -511,6 +513,53 @@ class FullImagesDataset(Dataset):
         spp_img = th.zeros(1, height, width, dtype=th.int32, device=dev)
         for t in tiles:
             spp_img[:, t["block_y"]:t["block_y"] + ts, t["block_x"]:t["block_x"] + ts] = d.spp
+        sample["spp"] = spp_img
+        return sample
+
+    def tile_positions(self, idx):
+        """[(file, block_x, block_y)] of scene `idx` from the 60-byte tile headers
+        (cached): what a rank needs to pick the tiles of its row band."""
+        cache = self.__dict__.setdefault("_positions", {})
+        if idx not in cache:
+            d = self.tiles_dset
+            start, end = d.indices[self.scenes[idx]]
+            found = []
+            for i in range(start, end):
+                fname = d._filename(i)
+                with open(fname, "rb") as fid:
+                    head = fid.read(_HEADER.size + 8)
+                d._parse_header(head[:_HEADER.size])
+                found.append((fname,) + struct.unpack_from("<2i", head, _HEADER.size))
+            cache[idx] = found
+        return cache[idx]
+
+    def read_rows(self, idx, y_lo, y_hi):
+        """Rows [y_lo, y_hi) of scene `idx`: same keys as `self[idx]` with tensors
+        [.., y_hi - y_lo, width].  Only the tiles that intersect the rows are read,
+        shipped and inflated -- the unit of multi-GPU sharding of the reader: tiles
+        are independent, so ranks split an image by rows without any exchange
+        (sbmc_b200.sharding.BandPlan gives the rows)."""
+        d = self.tiles_dset
+        if d.mode == TilesDataset.KPCN_MODE:
+            raise ValueError("read_rows serves the sample-based modes (sbmc / raw)")
+        height, width, ts = d.image_height, d.image_width, d.tile_size
+        if not 0 <= y_lo < y_hi <= height:
+            raise ValueError("rows [%d, %d) are not inside the image (%d rows)"
+                             % (y_lo, y_hi, height))
+        mine = [(f, bx, by) for f, bx, by in self.tile_positions(idx)
+                if by < y_hi and by + ts > y_lo]
+        if not mine:
+            raise ValueError("no tile of %s covers rows [%d, %d)" % (self.scenes[idx], y_lo, y_hi))
+        out, tiles = d._read_tiles([m[0] for m in mine], y_hi - y_lo, width, row0=y_lo)
+        dev = out["target_image"].device
+        first = tiles[0]["gfeatures"]
+        sample = {"global_features": d._global_features(first, dev),
+                  "scene_radius": first["scene_radius"]}
+        sample.update(out)
+        spp_img = th.zeros(1, y_hi - y_lo, width, dtype=th.int32, device=dev)
+        for t in tiles:
+            lo, hi = max(t["block_y"], y_lo) - y_lo, min(t["block_y"] + ts, y_hi) - y_lo
+            spp_img[:, lo:hi, t["block_x"]:t["block_x"] + ts] = d.spp
         sample["spp"] = spp_img
         return sample
 

@@ -27,7 +27,7 @@ from . import _lib
 
 __all__ = ["BandPlan", "exchange_halo", "reduce_halo", "kernel_weighting_fwd_sharded",
            "kernel_weighting_bwd_sharded", "ShardedKernelWeighting", "gather_bands",
-           "multisteps_forward_sharded", "multisteps_forward_halo"]
+           "multisteps_forward_sharded", "multisteps_forward_halo", "halo_mode_rows"]
 
 
 class BandPlan:
@@ -276,7 +276,16 @@ def multisteps_forward_sharded(model, samples, rank, world, overlap=144, group=N
     return {"radiance": full.movedim(0, -2).contiguous()}
 
 
-def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None):
+def halo_mode_rows(height, world, ksize, rank):
+    """Image rows [a, b) that `rank` needs as input in halo mode: its band plus
+    the K x K splat halo.  A rank can read just these from disk
+    (`FullImagesDataset.read_rows`) and pass `image_height=height, row0=a`."""
+    plan = BandPlan(height, world, ksize, align=4)
+    return plan.y0[rank] - plan.halo_top(rank), plan.y1[rank] + plan.halo_bot(rank)
+
+
+def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None,
+                            image_height=None, row0=0):
     """Tiled inference with halo EXCHANGE instead of full overlap recompute
     (inference pipeline of `Multisteps._forward_nhwc`, needs `model.bf16_chains`).
 
@@ -290,12 +299,17 @@ def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None
     (~39 px) because every step exchanges again.  Final all-gather of the bands.
     Same result as the unsharded forward up to the U-net's zero padding at
     distance >= unet_pad (exact when unet_pad covers the receptive field).
+
+    `samples` holds the full image by default; with `image_height` / `row0` it
+    holds only rows [row0, row0 + samples_rows) of an image of `image_height`
+    rows, which must cover `halo_mode_rows(...)` of this rank.
     """
     from . import conv1x1 as _c
     from . import unet_fast as _u
     from ._compat import crop_like
     radiance, features = samples["radiance"], samples["features"]
-    bs, spp, nf, height, w = features.shape
+    bs, spp, nf, local_rows, w = features.shape
+    height = local_rows if image_height is None else image_height
     k = model.ksize
     crop = (k - 1) // 2
     if unet_pad % 4 or not model._nhwc_pipeline_ok(nf):
@@ -307,8 +321,11 @@ def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None
     top, bot = plan.halo_top(rank), plan.halo_bot(rank)
     a, b = y0 - top, y1 + bot                          # rows of the chain / splat domain
     rows_ext, rows = b - a, y1 - y0
-    rad = radiance[..., a:b, :].to(dev)
-    feats = _c.to_nhwc_bf16(features[..., a:b, :].to(dev))        # [bs, spp, rows_ext*w, 128]
+    if a < row0 or b > row0 + local_rows:
+        raise ValueError("samples cover rows [%d, %d), rank %d needs [%d, %d)"
+                         % (row0, row0 + local_rows, rank, a, b))
+    rad = radiance[..., a - row0:b - row0, :].to(dev)
+    feats = _c.to_nhwc_bf16(features[..., a - row0:b - row0, :].to(dev))  # [bs, spp, rows_ext*w, 128]
     gf = samples["global_features"].to(dev).reshape(bs, -1).float()
     hw = rows_ext * w
     prop, ca = None, nf

@@ -47,12 +47,13 @@ int emul_tile_assemble_f32(const void *raw, const int64_t *tile_table, int64_t n
                            int64_t sample_stride_bytes, int ts, int spp, int sample_features,
                            int pixel_features, int path_depth, int flags, float *features,
                            float *radiance, float *low_spp, float *image_data,
-                           float *image_data_var, float *target_image, int64_t h, int64_t w) {
+                           float *image_data_var, float *target_image, int64_t h, int64_t w,
+                           int64_t row0) {
   sbmc::TileAssembleParams p;
   int rc = sbmc::tile_assemble_params(&p, raw, tile_table, ntiles, sample_stride_bytes, ts, spp,
                                       sample_features, pixel_features, path_depth, flags, features,
                                       radiance, low_spp, image_data, image_data_var, target_image,
-                                      h, w);
+                                      h, w, row0);
   if (rc == 1) return 0;
   if (rc < 0) return rc;
   const bool vec4 = (ts % 4 == 0) && (w % 4 == 0) && p.aligned16;

@@ -58,7 +58,7 @@ def emul():
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.emul_lz4_frames_inflate.argtypes = [vp, vp, i64, vp, vp]
     lib.emul_tile_assemble_f32.argtypes = [vp, vp, i64, i64, i32, i32, i32, i32, i32, i32,
-                                           vp, vp, vp, vp, vp, vp, i64, i64]
+                                           vp, vp, vp, vp, vp, vp, i64, i64, i64]
     lib.emul_last_error.restype = ctypes.c_char_p
     return lib
 
@@ -273,7 +273,7 @@ def test_oracle_reader_matches_reference_fixtures(name):
 
 
 # ------------------------------------------------------------------ device assembly code on the host
-def emul_read(files, kw, height, width, positions=None, force_scalar=False):
+def emul_read(files, kw, height, width, positions=None, force_scalar=False, row0=0):
     """sbmc_b200.datasets' host planning + the emulated kernels = the product
     path with the two launches replaced by their host builds."""
     d = datasets.TilesDataset(DATA, device="cpu", **kw)
@@ -305,7 +305,7 @@ def emul_read(files, kw, height, width, positions=None, force_scalar=False):
         datasets._align(d._sample_frame_bytes()), ts, spp, d.sample_features, d.pixel_features,
         d.path_depth, flags, out["features"].data_ptr(), out["radiance"].data_ptr(),
         out["low_spp"].data_ptr(), out["image_data"].data_ptr(), out["image_data_var"].data_ptr(),
-        out["target_image"].data_ptr(), height, width)
+        out["target_image"].data_ptr(), height, width, row0)
     assert rc == (1 if force_scalar else 4), (rc, lib.emul_last_error())
     return d, out, tiles
 
@@ -331,6 +331,20 @@ def test_emulated_kernels_match_reference_fixtures(name, force_scalar):
                        scene_radius=tiles[0]["gfeatures"]["scene_radius"],
                        global_features=d._global_features(tiles[0]["gfeatures"], "cpu"))
             check_item(exp, "%s/%d" % (name, i), out, i_diffuse_of(kw))
+
+
+@pytest.mark.parametrize("y_lo,y_hi", [(0, 16), (0, 5), (3, 11), (8, 16), (12, 13)])
+def test_emulated_row_band_equals_rows_of_the_full_image(y_lo, y_hi):
+    """Row-sharded reading: assembling rows [y_lo, y_hi) from the tiles that
+    intersect them gives exactly those rows of the whole image."""
+    files = fixture_files(False)[:4]
+    _, whole, _ = emul_read(files, {}, 16, 16)
+    full = datasets.FullImagesDataset(DATA, device="cpu")
+    mine = [f for f, bx, by in full.tile_positions(0) if by < y_hi and by + 8 > y_lo]
+    assert set(mine) <= set(files) and (len(mine) == 2) == (y_hi <= 8 or y_lo >= 8)
+    _, band, _ = emul_read(mine, {}, y_hi - y_lo, 16, row0=y_lo)
+    for k, v in whole.items():
+        assert th.equal(band[k], v[..., y_lo:y_hi, :]), k
 
 
 # ------------------------------------------------------------------ host logic of sbmc_b200.datasets
@@ -466,7 +480,8 @@ def test_reading_an_item_without_cuda_raises():
 
 def test_tile_assemble_argument_validation_needs_no_gpu():
     lib = _lib.load()
-    args = [None, None, 1, 0, 8, 3, 27, 30, 6, 31, None, None, None, None, None, None, 8, 8, None]
+    args = [None, None, 1, 0, 8, 3, 27, 30, 6, 31, None, None, None, None, None, None, 8, 8, 0,
+            None]
     assert lib.sbmc_tile_assemble_f32(*args) == -1 and b"null" in lib.sbmc_b200_last_error()
     args[6] = 26
     assert lib.sbmc_tile_assemble_f32(*args) == -1 and b"27" in lib.sbmc_b200_last_error()
@@ -578,6 +593,25 @@ def test_gpu_full_image_matches_oracle_on_larger_tiles(tmp_path, ts, tiles_x, ti
     by, bx = t["block_y"], t["block_x"]
     assert th.equal(t["radiance"], item["radiance"][..., by:by + ts, bx:bx + ts])
     assert th.equal(t["features"], item["features"][..., by:by + ts, bx:bx + ts])
+
+
+@pytest.mark.gpu
+def test_gpu_row_bands_tile_the_full_image():
+    """What each rank of a row-sharded job reads (BandPlan rows + halo)."""
+    from sbmc_b200.sharding import BandPlan
+    d = datasets.FullImagesDataset(DATA)
+    whole = d[1]
+    plan = BandPlan(16, 2, 5, align=4)
+    for rank in range(2):
+        lo = plan.y0[rank] - plan.halo_top(rank)
+        hi = plan.y1[rank] + plan.halo_bot(rank)
+        band = d.read_rows(1, lo, hi)
+        assert set(band) == set(whole)
+        for k, v in whole.items():
+            if isinstance(v, th.Tensor) and v.dim() >= 3 and v.shape[-1] == 16:
+                assert th.equal(band[k], v[..., lo:hi, :]), k
+    with pytest.raises(ValueError):
+        d.read_rows(0, 4, 4)
 
 
 @pytest.mark.gpu

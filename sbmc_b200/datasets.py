@@ -404,6 +404,30 @@ class TilesDataset(Dataset):
             sample = self._preprocess_kpcn(sample)
         return sample       # the sbmc-mode log compression ran inside the assembly kernel
 
+    def __getitems__(self, indices):
+        """Batched fetch (the DataLoader calls this once per batch when it exists):
+        all tiles of the batch are inflated and assembled by one pair of launches,
+        stacked along rows of one scratch image; every sample is its slice."""
+        indices = list(indices)
+        if self.mode == TilesDataset.KPCN_MODE or len(indices) <= 1:
+            return [self[i] for i in indices]
+        ts = self.tile_size
+        fnames = [self._filename(i) for i in indices]
+        out, tiles = self._read_tiles(fnames, ts * len(fnames), ts,
+                                      positions=[(0, i * ts) for i in range(len(fnames))])
+        dev = out["target_image"].device
+        samples = []
+        for i, t in enumerate(tiles):
+            sample = {"block_x": t["block_x"], "block_y": t["block_y"],
+                      "global_features": self._global_features(t["gfeatures"], dev)}
+            for k, v in out.items():
+                sample[k] = v[..., i * ts:(i + 1) * ts, :]
+            sample["spp"] = th.full((1, 1, 1), self.spp, dtype=th.int32, device=dev)
+            sample["scene_radius"] = t["gfeatures"]["scene_radius"]
+            sample["path"] = t["path"]
+            samples.append(sample)
+        return samples
+
     # -- [Bako2017] inputs (datasets.py:780-859); second caller, composed from torch ops --
     def _preprocess_kpcn(self, sample):
         src_f, tgt = sample["features"], sample["image_data"]

@@ -18,8 +18,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
 
 
+# The callers' tests build on the tile reader's: run the reader first, the scripts
+# last, so that a failure is reported where it originates (pytest -x stops early).
+_LATE = {"test_tiles.py": 1, "test_scripts.py": 2}
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
+    items.sort(key=lambda it: _LATE.get(os.path.basename(str(it.fspath)), 0))   # stable
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

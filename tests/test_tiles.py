@@ -347,6 +347,18 @@ def test_emulated_row_band_equals_rows_of_the_full_image(y_lo, y_hi):
         assert th.equal(band[k], v[..., y_lo:y_hi, :]), k
 
 
+def test_emulated_batched_layout_equals_single_tiles():
+    """TilesDataset.__getitems__ stacks the batch's tiles along rows of one scratch
+    image: each slice must equal the tile assembled alone."""
+    files = fixture_files(False)[2:7]
+    _, stacked, _ = emul_read(files, dict(spp=2), 8 * len(files), 8,
+                              positions=[(0, 8 * i) for i in range(len(files))])
+    for i, f in enumerate(files):
+        _, one, _ = emul_read([f], dict(spp=2), 8, 8, positions=[(0, 0)])
+        for k, v in one.items():
+            assert th.equal(stacked[k][..., 8 * i:8 * i + 8, :], v), (k, i)
+
+
 # ------------------------------------------------------------------ host logic of sbmc_b200.datasets
 def test_dataset_metadata_matches_the_reference():
     exp = expected()
@@ -612,6 +624,27 @@ def test_gpu_row_bands_tile_the_full_image():
                 assert th.equal(band[k], v[..., lo:hi, :]), k
     with pytest.raises(ValueError):
         d.read_rows(0, 4, 4)
+
+
+@pytest.mark.gpu
+def test_gpu_batched_fetch_equals_single_items():
+    """DataLoader batches go through TilesDataset.__getitems__ (one pair of
+    launches per batch) and must equal the items fetched one by one."""
+    from torch.utils.data import DataLoader
+    d = datasets.TilesDataset(DATA, spp=2)
+    before = _lib.launch_count()
+    batch = next(iter(DataLoader(d, batch_size=5, shuffle=False, num_workers=0)))
+    assert _lib.launch_count() == before + 2
+    assert batch["features"].shape == (5, 2, 93, 8, 8) and batch["spp"].shape == (5, 1, 1, 1)
+    for i in range(5):
+        one = d[i]
+        for k, v in one.items():
+            if isinstance(v, th.Tensor):
+                assert th.equal(batch[k][i], v), (k, i)
+            elif isinstance(v, str):
+                assert batch[k][i] == v
+            else:
+                assert batch[k][i].item() == pytest.approx(v)
 
 
 @pytest.mark.gpu

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--halo", action="store_true",
                     help="exchange U-net halos per step instead of recomputing a 144-row overlap")
     ap.add_argument("--unet-pad", type=int, default=64)
+    ap.add_argument("--data", help="root folder of scene folders with .bin tiles: every rank reads "
+                    "only the tiles of its row band (halo mode) instead of synthetic inputs")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -51,13 +53,35 @@ def main():
     # full frame is resident on every GPU so that only model + gather are timed
     gdev = "cpu" if a.check else dev
     g = th.Generator(device=gdev).manual_seed(1)
-    samples = {"radiance": th.rand(1, spp, 3, h, w, generator=g, device=gdev),
-               "features": th.randn(1, spp, nf, h, w, generator=g, device=gdev),
-               "global_features": th.randn(1, 3, 1, 1, generator=g, device=gdev)}
+    samples = None if a.data else {
+        "radiance": th.rand(1, spp, 3, h, w, generator=g, device=gdev),
+        "features": th.randn(1, spp, nf, h, w, generator=g, device=gdev),
+        "global_features": th.randn(1, 3, 1, 1, generator=g, device=gdev)}
+    row_kw = {}
+    if a.data:      # files -> each rank's band, read / inflated / assembled on its own GPU
+        from sbmc_b200 import datasets
+        assert a.halo, "--data feeds the halo mode"
+        dset = datasets.FullImagesDataset(a.data, spp=a.spp if not a.check else None)
+        h, w, spp, nf = dset.tiles_dset.image_height, dset.tiles_dset.image_width, dset.spp, \
+            dset.num_features
+        net = models.Multisteps(nf, 3).to(dev).eval().to(memory_format=th.channels_last)
+        net.bf16_chains = net.bf16_unet = True
+        if world > 1:
+            for prm in net.parameters():
+                dist.broadcast(prm.data, 0)
+        lo, hi = sharding.halo_mode_rows(h, world, net.ksize, rank)
+        t0 = time.perf_counter()
+        band = dset.read_rows(0, lo, hi)
+        th.cuda.synchronize()
+        print("rank %d read rows [%d, %d) in %.1f ms" % (rank, lo, hi, 1e3 * (time.perf_counter() - t0)),
+              flush=True)
+        samples = {k: band[k].unsqueeze(0) for k in ("radiance", "features", "global_features")}
+        row_kw = dict(image_height=h, row0=lo)
+
     def run():
         if a.halo:
             return sharding.multisteps_forward_halo(net, samples, rank, world,
-                                                    unet_pad=a.unet_pad)["radiance"]
+                                                    unet_pad=a.unet_pad, **row_kw)["radiance"]
         return sharding.multisteps_forward_sharded(net, samples, rank, world)["radiance"]
 
     with th.no_grad():
@@ -66,6 +90,10 @@ def main():
         out = run()
         if a.check:
             if rank == 0:
+                if a.data:
+                    whole = dset[0]
+                    samples = {k: whole[k].unsqueeze(0)
+                               for k in ("radiance", "features", "global_features")}
                 ref = net({k: v.to(dev) for k, v in samples.items()})["radiance"]
                 err = ((out - ref).norm() / ref.norm()).item()
                 mx = (out - ref).abs().max().item()

@@ -23,7 +23,7 @@
 // is needed.  One __syncwarp() per sequence publishes the bytes to the lanes
 // that read them next.
 //
-// The same source compiles for the host (tests/lz4_emul.cpp) with the lane
+// The same source compiles for the host (tests/native/tiles_emul.cpp) with the lane
 // loops run sequentially, so the cursor arithmetic is checked on CPU against
 // the reference library's own output; checksums are skipped, not verified.
 #pragma once
@@ -35,7 +35,11 @@
 #define SBMC_LZ4_PUBLISH() __syncwarp()
 #else
 #define SBMC_LZ4_FN static inline
+#if defined(SBMC_LZ4_REVERSE_LANES)  // host tests: lane order must not matter
+#define SBMC_LZ4_LANES(lane) for (int lane = 31; lane >= 0; --lane)
+#else
 #define SBMC_LZ4_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#endif
 #define SBMC_LZ4_PUBLISH() ((void)0)
 #endif
 
@@ -81,14 +85,15 @@ SBMC_LZ4_FN void match_lanes(uint8_t *dst, int64_t offset, int64_t n) {
     return;
   }
   SBMC_LZ4_LANES(lane) {
-    // i % offset without a division per byte: advance a running remainder.
-    int64_t i = lane;
-    int64_t r = lane % offset;
-    const int64_t step = 32 % offset;
-    for (; i < n; i += 32) {
+    // i % offset without a division per byte: advance a running remainder
+    // (offsets are 16-bit, so 32-bit arithmetic).
+    const uint32_t period = (uint32_t)offset;
+    uint32_t r = (uint32_t)lane % period;
+    const uint32_t step = 32u % period;
+    for (int64_t i = lane; i < n; i += 32) {
       dst[i] = from[r];
       r += step;
-      if (r >= offset) r -= offset;
+      if (r >= period) r -= period;
     }
   }
 }

@@ -44,16 +44,18 @@ needs_liblz4 = pytest.mark.skipif(tile_io.liblz4() is None, reason="system liblz
 
 
 # ------------------------------------------------------------------ helpers
-def emul():
-    """tests/native/tiles_emul.cpp built with g++ (device sources on the host)."""
+def emul(reverse_lanes=False):
+    """tests/native/tiles_emul.cpp built with g++ (device sources on the host);
+    `reverse_lanes` runs the 32 lanes of the inflater from 31 down to 0."""
     src = os.path.join(HERE, "native", "tiles_emul.cpp")
-    out = os.path.join(HERE, "native", "libtiles_emul.so")
+    out = os.path.join(HERE, "native", "libtiles_emul%s.so" % ("_rev" if reverse_lanes else ""))
     deps = [src] + [os.path.join(HERE, "..", "sbmc_b200", "csrc", f)
                     for f in ("lz4_warp.cuh", "tiles_body.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = "/usr/local/cuda/include"
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-I", cuda_inc, "-o", out, src])
+                               "-I", cuda_inc, "-o", out, src]
+                              + (["-DSBMC_LZ4_REVERSE_LANES"] if reverse_lanes else []))
     lib = ctypes.CDLL(out)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.emul_lz4_frames_inflate.argtypes = [vp, vp, i64, vp, vp]
@@ -94,14 +96,15 @@ def layout(frames, sizes):
     return np.array(table, np.int64).reshape(-1, 4), max(do, 16)
 
 
-def emul_inflate(frames, sizes):
+def emul_inflate(frames, sizes, reverse_lanes=False):
     table, total = layout(frames, sizes)
     src = np.frombuffer(b"".join(frames) + b"\0", np.uint8)
     dst = np.zeros(total, np.uint8)
     status = np.zeros(len(frames), np.int32)
     vp = ctypes.c_void_p
-    emul().emul_lz4_frames_inflate(src.ctypes.data_as(vp), table.ctypes.data_as(vp), len(frames),
-                                   dst.ctypes.data_as(vp), status.ctypes.data_as(vp))
+    emul(reverse_lanes).emul_lz4_frames_inflate(
+        src.ctypes.data_as(vp), table.ctypes.data_as(vp), len(frames), dst.ctypes.data_as(vp),
+        status.ctypes.data_as(vp))
     return [dst[t[2]:t[2] + t[3]].tobytes() for t in table], status
 
 
@@ -194,6 +197,10 @@ def test_lz4_oracle_and_emulated_warp_inflater_match_liblz4(opts):
     outs, status = emul_inflate(frames, [len(r) for r in raws])
     assert not status.any(), status
     assert outs == raws
+    # the copies of one sequence are independent of the order the lanes run in
+    # (on the GPU they run concurrently): same bytes with the lanes reversed
+    outs, status = emul_inflate(frames, [len(r) for r in raws], reverse_lanes=True)
+    assert not status.any() and outs == raws
 
 
 def test_lz4_default_preferences_are_the_reference_writers():

@@ -67,6 +67,19 @@ class _Staging(object):
 
 _STAGING = _Staging()
 
+# Threads that read tile files into the staging buffer (the only host work of an
+# item that scales with its size; `readinto` releases the GIL).
+_IO_THREADS = max(1, min(16, (os.cpu_count() or 1)))
+_POOL = None
+
+
+def _io_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=_IO_THREADS, thread_name_prefix="sbmc-tiles")
+    return _POOL
+
 
 class TilesDataset(Dataset):
     """Tiles stored one per .bin file (format: reference docstring,
@@ -268,29 +281,61 @@ class TilesDataset(Dataset):
                 flags |= bit
         return flags
 
+    def _needed_bytes(self, fname):
+        """Length of the file's prefix that holds the header and the first `spp`
+        sample chunks (the whole file when every sample is wanted)."""
+        size = os.path.getsize(fname)
+        if self.spp == self.sample_count:
+            return size
+        pos = _HEADER.size + 8
+        with open(fname, "rb") as fid:
+            for _ in range(1 + self.spp):
+                fid.seek(pos)
+                head = fid.read(4)
+                if len(head) < 4:
+                    return size             # truncated: the parser reports it
+                (nbytes,) = struct.unpack("<i", head)
+                if nbytes < 0:
+                    return size
+                pos += 4 + nbytes
+        return min(pos, size)
+
     def _plan(self, fnames):
-        """Reads the files into the pinned staging buffer and walks their chunk
-        headers.  Returns (staging view, frame table rows, per-tile records)."""
-        sizes = [os.path.getsize(f) for f in fnames]
-        stage = _STAGING.get(sum(_align(s, 16) for s in sizes))
+        """Reads the files (only the chunks of the first `spp` samples) into the
+        pinned staging buffer -- in parallel, file reads release the GIL -- and
+        walks their chunk headers.  Returns (staging view, frame table rows,
+        per-tile records, inflated bytes)."""
+        workers = min(_IO_THREADS, len(fnames))
+        pool = _io_pool() if workers > 1 else None
+        needed = list(pool.map(self._needed_bytes, fnames)) if pool else \
+            [self._needed_bytes(f) for f in fnames]
+        offsets, total = [], 0
+        for need in needed:
+            offsets.append(total)
+            total += _align(need, 16)
+        stage = _STAGING.get(total)
         host = stage.numpy()
-        ts_bytes = None
+
+        def read(job):
+            fname, off, need = job
+            with open(fname, "rb") as fid:
+                return fid.readinto(memoryview(host[off:off + need]))
+
+        jobs = list(zip(fnames, offsets, needed))
+        gots = list(pool.map(read, jobs)) if pool else [read(j) for j in jobs]
+
+        ts = self.tile_size
+        ts_bytes = (self.pixel_features * ts * ts * 4, self._sample_frame_bytes())
         frames, tiles = [], []
-        src = 0      # offset in the staging buffer
         dst = 0      # offset in the inflated buffer
-        for fname, size in zip(fnames, sizes):
+        for fname, src, got in zip(fnames, offsets, gots):
             try:
-                with open(fname, "rb") as fid:
-                    got = fid.readinto(memoryview(host[src:src + size]))
                 view = host[src:src + got]
                 try:
                     gfeatures = self._parse_header(view[:_HEADER.size].tobytes())
                 except struct.error:
                     LOG.error("reading meta for file %s failed", fname)
                     raise
-                if ts_bytes is None:
-                    ts = self.tile_size
-                    ts_bytes = (self.pixel_features * ts * ts * 4, self._sample_frame_bytes())
                 pos = _HEADER.size
                 try:
                     block_x, block_y = struct.unpack_from("<2i", view, pos)
@@ -317,8 +362,7 @@ class TilesDataset(Dataset):
                 LOG.error("could not read %s", fname)
                 raise
             tiles.append(record)
-            src += _align(pos, 16)      # chunks past `spp` are not shipped: overwritten next
-        return stage[:max(src, 1)], frames, tiles, dst
+        return stage[:max(total, 1)], frames, tiles, dst
 
     def _read_tiles(self, fnames, height, width, positions=None, row0=0):
         """Inflates and assembles `fnames` into one set of [.., height, width]

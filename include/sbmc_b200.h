@@ -216,8 +216,8 @@ SBMC_API int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void *
  * frame_table (device) is int64 [nframes][4] = {source byte offset in src,
  * source byte count, destination byte offset in dst, expected inflated size};
  * status (device, int32 [nframes]) receives 0 or an SBMC_LZ4_* code per frame
- * (the call itself only fails for bad arguments / launch errors).  Frame and
- * block checksums are skipped, not verified. */
+ * (the call itself only fails for bad arguments / launch errors).  Header,
+ * block and content checksums (xxHash32) are verified when the frame has them. */
 #define SBMC_LZ4_OK 0
 #define SBMC_LZ4_BAD_MAGIC 1
 #define SBMC_LZ4_BAD_HEADER 2
@@ -226,6 +226,7 @@ SBMC_API int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void *
 #define SBMC_LZ4_BAD_OFFSET 5
 #define SBMC_LZ4_SIZE_MISMATCH 6
 #define SBMC_LZ4_BLOCK_TOO_LARGE 7
+#define SBMC_LZ4_BAD_CHECKSUM 8
 SBMC_API int sbmc_lz4_frames_inflate(const void *src, const int64_t *frame_table,
                                      int64_t nframes, void *dst, int32_t *status,
                                      void *stream);

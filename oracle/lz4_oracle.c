@@ -10,8 +10,7 @@
  * and cuda-sbmc.dockerfile:19; the writer is LZ4F_compressFrame with default
  * preferences, pbrt_patches/sbmc_pbrt.diff:6140-6158).  This file restates the
  * published LZ4 frame format (v1.6.x) and block format: sequential, one byte at
- * a time, and -- unlike the device inflater -- it verifies the xxHash32 header,
- * block and content checksums.
+ * a time, verifying the xxHash32 header, block and content checksums.
  *
  * PARITY PIN: tests/test_tiles.py checks it against frames produced by the real
  * liblz4 (LZ4F_compressFrame through ctypes on /usr/lib/x86_64-linux-gnu/liblz4.so.1,

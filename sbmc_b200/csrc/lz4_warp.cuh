@@ -25,7 +25,8 @@
 //
 // The same source compiles for the host (tests/native/tiles_emul.cpp) with the lane
 // loops run sequentially, so the cursor arithmetic is checked on CPU against
-// the reference library's own output; checksums are skipped, not verified.
+// the reference library's own output.  Header, block and content checksums
+// (xxHash32) are verified like `lz4.frame.decompress` does.
 #pragma once
 #include <stdint.h>
 
@@ -55,10 +56,53 @@ enum Status : int {
   kBadOffset = 5,     // match offset 0 or beyond the produced output
   kSizeMismatch = 6,  // decoded size differs from the size the tile header implies
   kBlockTooLarge = 7, // block larger than the frame's declared maximum
+  kBadChecksum = 8,   // header / block / content xxHash32 mismatch
 };
 
 SBMC_LZ4_FN uint32_t load_u32(const uint8_t *p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// xxHash32 (seed 0) of p[0..len): the checksum of the frame format.  Computed
+// by every lane alike (uniform loads broadcast), so the result is warp-uniform
+// without a shuffle; only frames that carry checksums pay for it (the
+// reference's writer emits none besides the 1-byte header check).
+SBMC_LZ4_FN uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+SBMC_LZ4_FN uint32_t xxh32(const uint8_t *p, int64_t len) {
+  const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u,
+                 P5 = 374761393u;
+  const uint8_t *const end = p + len;
+  uint32_t h;
+  if (len >= 16) {
+    uint32_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0u - P1;
+    const uint8_t *const limit = end - 16;
+    do {
+      v1 = rotl32(v1 + load_u32(p) * P2, 13) * P1;
+      v2 = rotl32(v2 + load_u32(p + 4) * P2, 13) * P1;
+      v3 = rotl32(v3 + load_u32(p + 8) * P2, 13) * P1;
+      v4 = rotl32(v4 + load_u32(p + 12) * P2, 13) * P1;
+      p += 16;
+    } while (p <= limit);
+    h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+  } else {
+    h = P5;
+  }
+  h += (uint32_t)len;
+  while (p + 4 <= end) {
+    h = rotl32(h + load_u32(p) * P3, 17) * P4;
+    p += 4;
+  }
+  while (p < end) {
+    h = rotl32(h + (uint32_t)(*p) * P5, 11) * P1;
+    ++p;
+  }
+  h ^= h >> 15;
+  h *= P2;
+  h ^= h >> 13;
+  h *= P3;
+  h ^= h >> 16;
+  return h;
 }
 
 // Copies n bytes src -> dst, lanes interleaved byte-wise (32 consecutive bytes
@@ -177,9 +221,11 @@ SBMC_LZ4_FN int decode_frames(const uint8_t *src, int64_t src_len, uint8_t *dst,
     const int size_id = (bd >> 4) & 7;
     if (size_id < 4) return kBadHeader;
     const int64_t block_max = (int64_t)1 << (8 + 2 * size_id);
-    const int64_t skip = (has_size ? 8 : 0) + (has_dict ? 4 : 0) + 1;  // + header checksum
-    if (skip > end - ip) return kTruncated;
+    const int64_t skip = (has_size ? 8 : 0) + (has_dict ? 4 : 0);
+    if (skip + 1 > end - ip) return kTruncated;
     ip += skip;
+    if (((xxh32(ip - skip - 2, skip + 2) >> 8) & 0xFFu) != *ip) return kBadChecksum;
+    ++ip;  // header checksum byte
     const int64_t frame_start = op;
     for (;;) {
       if (end - ip < 4) return kTruncated;
@@ -198,14 +244,16 @@ SBMC_LZ4_FN int decode_frames(const uint8_t *src, int64_t src_len, uint8_t *dst,
         const int rc = decode_block(ip, ip + bsize, dst, &op, dst_cap, independent ? op : frame_start);
         if (rc != kOk) return rc;
       }
-      ip += bsize;
-      if (block_sum) {
-        if (end - ip < 4) return kTruncated;
+      if (block_sum) {  // xxHash32 of the block as stored
+        if (end - ip - bsize < 4) return kTruncated;
+        if (load_u32(ip + bsize) != xxh32(ip, bsize)) return kBadChecksum;
         ip += 4;
       }
+      ip += bsize;
     }
-    if (content_sum) {
+    if (content_sum) {  // xxHash32 of the frame's inflated bytes
       if (end - ip < 4) return kTruncated;
+      if (load_u32(ip) != xxh32(dst + frame_start, op - frame_start)) return kBadChecksum;
       ip += 4;
     }
     ++frames;

@@ -42,7 +42,7 @@ _META_FIELDS = ("version", "tile_size", "image_width", "image_height", "sample_c
 _LZ4_ERRORS = {1: "not an LZ4 frame", 2: "unsupported LZ4 frame header", 3: "truncated frame",
                4: "frame larger than the tile header implies", 5: "invalid match offset",
                6: "inflated size differs from what the tile header implies",
-               7: "block exceeds the frame's maximum block size"}
+               7: "block exceeds the frame's maximum block size", 8: "checksum mismatch"}
 # flags of sbmc_tile_assemble_f32 (include/sbmc_b200.h)
 _F_COORDS, _F_GBUFFER, _F_P, _F_LD, _F_BT, _F_LOG, _F_ALIGNED = 1, 2, 4, 8, 16, 32, 64
 

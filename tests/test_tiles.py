@@ -242,6 +242,27 @@ def test_lz4_error_statuses():
     outs, status = emul_inflate([c[0] for c in cases], [c[1] for c in cases])
     assert list(status) == [c[2] for c in cases]
     assert outs[5] == raw + raw and outs[6] == raw
+    # checksums are verified like lz4.frame.decompress does: header byte always,
+    # block / content xxHash32 when the frame carries them
+    hdr = bytearray(tile_io.stored_frame(raw))
+    hdr[6] ^= 0xFF
+    sums = []
+    if tile_io.liblz4() is not None:
+        good = tile_io.compress_frame(raw, content_checksum=True, block_checksum=True)
+        flipped = bytearray(good)
+        flipped[len(good) // 2] ^= 0x01            # inside a block: malformed or checksum error
+        tail = bytearray(good)
+        tail[-1] ^= 0x01                           # the content checksum itself
+        only_content = bytearray(tile_io.compress_frame(raw, content_checksum=True))
+        only_content[20] ^= 0x01                   # a literal byte: inflates, hash differs
+        sums = [bytes(flipped), bytes(tail), bytes(only_content), good]
+    outs2, status2 = emul_inflate([bytes(hdr)] + sums, [n] * (1 + len(sums)))
+    assert status2[0] == 8
+    if sums:
+        assert status2[1] != 0 and list(status2[2:]) == [8, 8, 0]
+    for blob in sums[:3]:
+        with pytest.raises(RuntimeError):
+            tile_io.decompress_frame(blob)         # the real library rejects them too
     with pytest.raises(oracle.Lz4Error):
         oracle.lz4_frame_decompress(frame[:len(frame) // 2])
     bad = bytearray(tile_io.stored_frame(raw))
@@ -550,11 +571,20 @@ def test_gpu_inflater_error_statuses_match_the_emulation():
     raw = (b"sample-based monte carlo denoising " * 400)
     frame = tile_io.compress_frame(raw) if tile_io.liblz4() else tile_io.stored_frame(raw)
     n = len(raw)
+    hdr = bytearray(tile_io.stored_frame(raw))
+    hdr[6] ^= 0xFF                                   # header checksum byte
     cases = [(frame[:len(frame) // 2], n), (b"\0\0\0\0junk", 10), (frame, n - 1), (frame, n + 1),
-             (frame + frame, 2 * n), (frame, n)]
+             (frame + frame, 2 * n), (frame, n), (bytes(hdr), n)]
+    expect = [3, 1, 4, 6, 0, 0, 8]
+    if tile_io.liblz4() is not None:
+        good = tile_io.compress_frame(raw, content_checksum=True, block_checksum=True)
+        bad = bytearray(good)
+        bad[-1] ^= 0x01                              # content checksum
+        cases += [(good, n), (bytes(bad), n)]
+        expect += [0, 8]
     _, want = emul_inflate([c[0] for c in cases], [c[1] for c in cases])
     outs, got = _gpu_inflate([c[0] for c in cases], [c[1] for c in cases])
-    assert list(got) == list(want) == [3, 1, 4, 6, 0, 0]
+    assert list(got) == list(want) == expect
     assert outs[4] == raw + raw and outs[5] == raw
 
 

@@ -87,7 +87,8 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_SPLAT_BWD 6    /* fused ProgressiveKernelApply backward  */
 #define SBMC_KERNEL_CONV1X1 7      /* fused 3-layer 1x1 ConvChain (tcgen05)  */
 #define SBMC_KERNEL_TILES 8        /* tile reader: LZ4 inflate + assembly    */
-#define SBMC_NUM_KERNEL_KINDS 9
+#define SBMC_KERNEL_OPTIM 9        /* fused gradient clipping + Adam         */
+#define SBMC_NUM_KERNEL_KINDS 10
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
 
@@ -264,6 +265,36 @@ SBMC_API int sbmc_tile_assemble_f32(const void *raw, const int64_t *tile_table, 
                                     float *low_spp, float *image_data, float *image_data_var,
                                     float *target_image, int64_t h, int64_t w, int64_t row0,
                                     void *stream);
+
+/* ---- fused optimizer step of the training interface ---------------------- *
+ * sbmc/interfaces.py:78-106 clips the gradient norm at 1000
+ * (torch.nn.utils.clip_grad_norm_) and steps Adam over every parameter tensor
+ * of the model; these two entry points do both over ALL tensors in three
+ * launches.  Device tables built by the caller: tensors int64 [ntensors][5] =
+ * {param, grad, exp_avg, exp_avg_sq (fp32 device pointers), numel}; chunks int64
+ * [nchunks][2] = {tensor index, first element}, one chunk per
+ * SBMC_MT_CHUNK_ELEMS elements of a tensor. */
+#define SBMC_MT_CHUNK_ELEMS 65536
+
+/* norm_and_coef[0] = ||all gradients||_2, norm_and_coef[1] = min(1, max_norm /
+ * (norm + 1e-6)) (device, 2 floats); partial: device scratch of nchunks floats.
+ * Deterministic (no atomics). */
+SBMC_API int sbmc_multi_tensor_grad_norm_f32(const int64_t *tensors, const int64_t *chunks,
+                                             int64_t nchunks, float *partial, float max_norm,
+                                             float *norm_and_coef, void *stream);
+
+/* torch.optim.Adam's update (no weight decay, no amsgrad) on every element:
+ *   g *= *clip_coef (written back when != 1; clip_coef may be NULL = no clipping)
+ *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g g
+ *   p -= lr / bias_correction1 * m / (sqrt(v) / bias_correction2_sqrt + eps)
+ * with bias_correction1 = 1 - beta1^step, bias_correction2_sqrt = sqrt(1 - beta2^step).
+ * Hyper-parameters are doubles: the fp32 constants of the update (1 - beta2, lr /
+ * bias_correction1, ...) are derived in double like torch derives them. */
+SBMC_API int sbmc_multi_tensor_adam_f32(const int64_t *tensors, const int64_t *chunks,
+                                        int64_t nchunks, const float *clip_coef, double lr,
+                                        double beta1, double beta2, double eps,
+                                        double bias_correction1, double bias_correction2_sqrt,
+                                        void *stream);
 
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /

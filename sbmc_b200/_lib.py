@@ -47,6 +47,10 @@ SIGNATURES = {
     "sbmc_tile_assemble_f32":
         (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _ptr,
                 _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr]),
+    "sbmc_multi_tensor_grad_norm_f32":
+        (_int, [_ptr, _ptr, _i64, _ptr, ctypes.c_float, _ptr, _ptr]),
+    "sbmc_multi_tensor_adam_f32":
+        (_int, [_ptr, _ptr, _i64, _ptr] + [ctypes.c_double] * 6 + [_ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),
@@ -115,8 +119,8 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain", 8: "tiles"}
-NUM_KERNEL_KINDS = 9
+                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain", 8: "tiles", 9: "optim"}
+NUM_KERNEL_KINDS = 10
 
 
 def timing_enable(flag):

@@ -20,14 +20,21 @@ _GRAD_CLIP = 1000
 
 class SampleBasedDenoiserInterface(object):
     """model: nn.Module taking / returning dicts; lr: Adam step size; cuda: move
-    the model (and every batch) to the GPU."""
+    the model (and every batch) to the GPU; fused_optimizer: see below."""
 
-    def __init__(self, model, lr=1e-4, cuda=False):
+    def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False):
         self.model = model.cuda() if cuda else model
         self.device = "cuda" if cuda else "cpu"
         self.loss_fn = losses.TonemappedRelativeMSE()
         self.rmse_fn = losses.RelativeMSE()
-        self.optimizer = th.optim.Adam(self.model.parameters(), lr=lr)
+        # fused_optimizer (extra, CUDA only): clipping + Adam over all parameter
+        # tensors in three launches (sbmc_b200.optim.FusedAdam)
+        self.fused_optimizer = bool(fused_optimizer)
+        if self.fused_optimizer:
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(self.model.parameters(), lr=lr)
+        else:
+            self.optimizer = th.optim.Adam(self.model.parameters(), lr=lr)
 
     # -- helpers -----------------------------------------------------------------
     def _to_device(self, batch):
@@ -56,10 +63,15 @@ class SampleBasedDenoiserInterface(object):
             kind = "NaN" if math.isnan(value) else "Infinite"
             LOG.error("%s loss, there might be outliers in the data.", kind)
             raise RuntimeError("%s loss at train time." % kind)
-        norm = th.nn.utils.clip_grad_norm_(self.model.parameters(), _GRAD_CLIP)
+        if self.fused_optimizer:
+            self.optimizer.step(max_norm=_GRAD_CLIP)
+            norm = self.optimizer.last_grad_norm[0]
+        else:
+            norm = th.nn.utils.clip_grad_norm_(self.model.parameters(), _GRAD_CLIP)
         if norm > _GRAD_CLIP:
             LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, float(norm))
-        self.optimizer.step()
+        if not self.fused_optimizer:
+            self.optimizer.step()
         with th.no_grad():
             rmse = self.rmse_fn(out, tgt).item()
         return {"loss": value, "rmse": rmse}

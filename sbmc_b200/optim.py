@@ -1,0 +1,116 @@
+"""Fused gradient clipping + Adam: the optimizer half of the training step.
+
+The reference's step (sbmc/interfaces.py:78-106) is `loss.backward()`,
+`clip_grad_norm_(params, 1000)`, `Adam.step()`: on the ~150 parameter tensors of
+`Multisteps` eager PyTorch spends hundreds of small launches on the last two.
+`FusedAdam.step(max_norm=...)` does them in three launches over device tables of
+all tensors (`sbmc_multi_tensor_grad_norm_f32`, `sbmc_multi_tensor_adam_f32`),
+without a host synchronisation: the clip coefficient stays on the device.
+
+Same hyper-parameters, update rule and state layout (`step`, `exp_avg`,
+`exp_avg_sq`) as `torch.optim.Adam` without weight decay / amsgrad, so state dicts
+interchange.  CUDA fp32 parameters only; anything else raises (no fallback).
+"""
+import math
+
+import torch as th
+
+from . import _lib
+
+__all__ = ["FusedAdam"]
+
+_CHUNK = 65536      # SBMC_MT_CHUNK_ELEMS (include/sbmc_b200.h)
+
+
+class FusedAdam(th.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
+            raise ValueError("invalid Adam hyper-parameters")
+        super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.last_grad_norm = None      # device tensor [2]: norm, clip coefficient
+
+    @staticmethod
+    def _tables(rows, dev):
+        """rows: [(param, grad, exp_avg, exp_avg_sq)] -> device tables."""
+        tensors, chunks = [], []
+        for t, (p, g, m, v) in enumerate(rows):
+            n = p.numel()
+            tensors.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n))
+            chunks.extend((t, start) for start in range(0, n, _CHUNK))
+        host = th.tensor(tensors, dtype=th.int64).reshape(-1, 5)
+        hchunks = th.tensor(chunks, dtype=th.int64).reshape(-1, 2)
+        if dev.type == "cuda":
+            host, hchunks = host.pin_memory(), hchunks.pin_memory()
+        return host.to(dev, non_blocking=True), hchunks.to(dev, non_blocking=True), len(chunks)
+
+    @th.no_grad()
+    def step(self, closure=None, max_norm=None):
+        """One Adam step on every parameter that has a gradient.  With `max_norm`
+        the gradients are first scaled by min(1, max_norm / (total norm + 1e-6))
+        like `clip_grad_norm_`; the norm / coefficient are left in
+        `self.last_grad_norm` (device tensor, read it only when needed)."""
+        loss = None
+        if closure is not None:
+            with th.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        coef_ptr = None
+        groups = []
+        everything = []
+        for group in self.param_groups:
+            rows = []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                g = p.grad
+                if not (p.is_cuda and p.dtype == th.float32 and p.is_contiguous()
+                        and g.dtype == th.float32 and g.is_contiguous() and g.device == p.device
+                        and not g.is_sparse):
+                    raise _lib.SbmcB200Error(
+                        "FusedAdam wants contiguous float32 CUDA parameters and gradients")
+                state = self.state[p]
+                if not state:
+                    state["step"] = th.zeros((), dtype=th.float32)
+                    state["exp_avg"] = th.zeros_like(p, memory_format=th.contiguous_format)
+                    state["exp_avg_sq"] = th.zeros_like(p, memory_format=th.contiguous_format)
+                rows.append((p, g, state["exp_avg"], state["exp_avg_sq"]))
+            if rows:
+                groups.append((group, rows))
+                everything.extend(rows)
+        if not everything:
+            return loss
+        dev = everything[0][0].device
+        if any(r[0].device != dev for r in everything):
+            raise _lib.SbmcB200Error("FusedAdam: all parameters must live on one device")
+        # tensors that have taken the same number of steps share one launch
+        parts = []
+        for group, rows in groups:
+            by_step = {}
+            for r in rows:
+                by_step.setdefault(float(self.state[r[0]]["step"]), []).append(r)
+            parts.extend((group, step, part) for step, part in sorted(by_step.items()))
+        with th.cuda.device(dev):
+            stream = th.cuda.current_stream().cuda_stream
+            tables = None
+            if max_norm is not None:
+                tables = self._tables(everything, dev)
+                tensors, chunks, nchunks = tables
+                partial = th.empty(max(nchunks, 1), dtype=th.float32, device=dev)
+                self.last_grad_norm = th.empty(2, dtype=th.float32, device=dev)
+                _lib.check(lib.sbmc_multi_tensor_grad_norm_f32(
+                    tensors.data_ptr(), chunks.data_ptr(), nchunks, partial.data_ptr(),
+                    float(max_norm), self.last_grad_norm.data_ptr(), stream), "grad_norm")
+                coef_ptr = self.last_grad_norm.data_ptr() + 4
+            for group, step, part in parts:
+                beta1, beta2 = group["betas"]
+                t = step + 1
+                if tables is None or len(parts) > 1:
+                    tables = self._tables(part, dev)
+                tensors, chunks, nchunks = tables
+                _lib.check(lib.sbmc_multi_tensor_adam_f32(
+                    tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, group["lr"],
+                    beta1, beta2, group["eps"], 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t),
+                    stream), "adam")
+                for r in part:
+                    self.state[r[0]]["step"] += 1
+        return loss

@@ -62,7 +62,8 @@ def main(args):
 
     meta = dict(model_params=model_params, kpcn_mode=args.kpcn_mode, data_params=data_args)
     LOG.info("Model configuration: %s", model_params)
-    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=True)
+    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=True,
+                                                        fused_optimizer=args.fused_optimizer)
     checkpointer = _compat.Checkpointer(args.checkpoint_dir, model, meta=meta,
                                         optimizers=interface.optimizer)
     checkpointer.load_latest()
@@ -86,6 +87,8 @@ def parser():
     p.add_argument("--num_epochs", type=int)
     p.add_argument("--max_steps", type=int, help="stop after this many steps (extra).")
     p.add_argument("--log_every", type=int, default=50)
+    p.add_argument("--fused_optimizer", action="store_true",
+                   help="clip + Adam over all tensors in three launches (extra).")
     p.add_argument("--spp", type=int, default=8, help="Max number of samples per pixel.")
     p.add_argument("--kpcn_mode", dest="kpcn_mode", action="store_true", default=False)
     p.add_argument("--gather", dest="gather", action="store_true", default=False)

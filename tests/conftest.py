@@ -18,9 +18,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
 
 
-# The callers' tests build on the tile reader's: run the reader first, the scripts
-# last, so that a failure is reported where it originates (pytest -x stops early).
-_LATE = {"test_tiles.py": 1, "test_scripts.py": 2}
+# The callers' tests build on the hot path's: run the hot path first, then the tile
+# reader, the optimizer and the scripts (which use both) last, so that a failure
+# is reported where it originates (pytest -x stops early).
+_LATE = {"test_tiles.py": 1, "test_optim.py": 2, "test_scripts.py": 3}
 
 
 def pytest_collection_modifyitems(config, items):

@@ -10,6 +10,7 @@ timeout 900 python -m pytest tests/test_tiles.py tests/test_scripts.py -m gpu -q
 echo "== sanitizer on the tile kernels"
 timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_tiles.py -m gpu -q -x \
   -k "inflater or fixtures" 2>&1 | tail -8 | tee gpurun_out/${tag}_sanitizer_tiles.txt
+echo "== optimizer tests"; timeout 600 python -m pytest tests/test_optim.py -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/${tag}_pytest_optim.txt
 echo "== pytest gpu (all)"; timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/${tag}_pytest.txt
 echo "== tiles bench"; timeout 900 python benchmarks/tiles_bench.py 2>&1 | grep "^{" | tee gpurun_out/${tag}_tiles_bench.json | cut -c1-600
 echo "== ncu tiles"

@@ -81,6 +81,44 @@ def _io_pool():
     return _POOL
 
 
+class _CudaBackend(object):
+    """Where the two launches of an item run: libsbmc_b200's kernels on a CUDA
+    device.  (The only backend of the product; the test-suite swaps in the device
+    sources compiled for the host, tests/native/tiles_emul.cpp, to exercise the
+    Python side of this module on machines without a GPU.)"""
+
+    def __init__(self, device):
+        if device is not None:
+            self.device = th.device(device)
+        elif th.cuda.is_available():
+            self.device = th.device("cuda", th.cuda.current_device())
+        else:
+            self.device = None
+        if self.device is None or self.device.type != "cuda" or not th.cuda.is_available():
+            raise _lib.SbmcB200Error(
+                "sbmc_b200.datasets inflates and assembles tiles on the GPU; no CUDA device is "
+                "available and there is no CPU data path")
+        self.lib = _lib.load()
+
+    def scope(self):
+        return th.cuda.device(self.device)
+
+    def _stream(self):
+        return th.cuda.current_stream(self.device).cuda_stream
+
+    def inflate(self, comp, table, nframes, raw, status):
+        _lib.check(self.lib.sbmc_lz4_frames_inflate(
+            comp.data_ptr(), table.data_ptr(), nframes, raw.data_ptr(), status.data_ptr(),
+            self._stream()), "lz4_frames_inflate")
+
+    def assemble(self, *args):
+        _lib.check(self.lib.sbmc_tile_assemble_f32(*(args + (self._stream(),))), "tile_assemble")
+
+
+def _backend(device):
+    return _CudaBackend(device)
+
+
 class TilesDataset(Dataset):
     """Tiles stored one per .bin file (format: reference docstring,
     datasets.py:36-155).  `path` is a .txt list of .bin files or a root folder of
@@ -259,15 +297,6 @@ class TilesDataset(Dataset):
         return g
 
     # -- the GPU read path ----------------------------------------------------------------
-    def _device(self):
-        if self.device is not None:
-            return th.device(self.device)
-        if not th.cuda.is_available():
-            raise _lib.SbmcB200Error(
-                "sbmc_b200.datasets inflates and assembles tiles on the GPU; no CUDA device is "
-                "available and there is no CPU data path")
-        return th.device("cuda", th.cuda.current_device())
-
     def _sample_frame_bytes(self):
         ts, depth = self.tile_size, self.path_depth
         return (self.sample_features + 6 * depth) * ts * ts * 4 + depth * ts * ts * 2
@@ -364,34 +393,34 @@ class TilesDataset(Dataset):
             tiles.append(record)
         return stage[:max(total, 1)], frames, tiles, dst
 
-    def _read_tiles(self, fnames, height, width, positions=None, row0=0):
+    def _read_tiles(self, fnames, height, width, positions=None, row0=0, clip_rows=False):
         """Inflates and assembles `fnames` into one set of [.., height, width]
-        tensors holding image rows row0 .. row0 + height - 1 (tile rows outside are
-        skipped); `positions` overrides the tiles' (block_x, block_y)."""
-        dev = self._device()
-        lib = _lib.load()
+        tensors holding image rows row0 .. row0 + height - 1; `positions` overrides
+        the tiles' (block_x, block_y).  With `clip_rows` tiles may stick out of the
+        row range (their rows outside are skipped: a rank's band), otherwise every
+        tile must fit."""
+        backend = _backend(self.device)
+        dev = backend.device
         stage, frames, tiles, raw_bytes = self._plan(fnames)
         ts, spp = self.tile_size, self.spp
         nchans = self.pixel_features // 2
         nf = len(self.labels)
-        with th.cuda.device(dev):
-            stream = th.cuda.current_stream()
+        rows = []
+        aligned = True
+        for i, t in enumerate(tiles):
+            bx, by = positions[i] if positions is not None else (t["block_x"], t["block_y"])
+            fits = by >= row0 and by + ts <= row0 + height
+            if bx < 0 or by < 0 or bx + ts > width or not (fits or clip_rows):
+                raise ValueError("tile %s at (%d, %d) does not fit a %dx%d image"
+                                 % (t["path"], bx, by, width, height))
+            aligned &= bx % 4 == 0
+            rows.append((t["image_off"], t["samples_off"], bx, by))
+        with backend.scope():
             comp = stage.to(dev, non_blocking=True)
             table = th.tensor(frames, dtype=th.int64).reshape(-1, 4).to(dev, non_blocking=True)
             raw = th.empty(max(raw_bytes, 16), dtype=th.uint8, device=dev)
             status = th.empty(len(frames), dtype=th.int32, device=dev)
-            _lib.check(lib.sbmc_lz4_frames_inflate(
-                comp.data_ptr(), table.data_ptr(), len(frames), raw.data_ptr(), status.data_ptr(),
-                stream.cuda_stream), "lz4_frames_inflate")
-            rows = []
-            aligned = True
-            for i, t in enumerate(tiles):
-                bx, by = positions[i] if positions is not None else (t["block_x"], t["block_y"])
-                if bx < 0 or by < 0 or bx + ts > width or (row0 == 0 and by + ts > height):
-                    raise ValueError("tile %s at (%d, %d) does not fit a %dx%d image"
-                                     % (t["path"], bx, by, width, height))
-                aligned &= bx % 4 == 0
-                rows.append((t["image_off"], t["samples_off"], bx, by))
+            backend.inflate(comp, table, len(frames), raw, status)
             tile_table = th.tensor(rows, dtype=th.int64).reshape(-1, 4).to(dev, non_blocking=True)
             whole = len(tiles) == 1 and height == ts and width == ts
             alloc = th.empty if whole else th.zeros      # uncovered pixels stay 0 (datasets.py:944)
@@ -403,13 +432,12 @@ class TilesDataset(Dataset):
                 out["radiance"] = alloc(spp, 3, height, width, device=dev)
                 out["low_spp"] = alloc(3, height, width, device=dev)
             ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
-            _lib.check(lib.sbmc_tile_assemble_f32(
+            backend.assemble(
                 raw.data_ptr(), tile_table.data_ptr(), len(tiles), _align(self._sample_frame_bytes()),
                 ts, spp, self.sample_features, self.pixel_features, self.path_depth,
                 self._flags() | (_F_ALIGNED if aligned else 0), ptr("features"), ptr("radiance"),
                 ptr("low_spp"), out["image_data"].data_ptr(), out["image_data_var"].data_ptr(),
-                out["target_image"].data_ptr(), height, width, row0, stream.cuda_stream),
-                "tile_assemble")
+                out["target_image"].data_ptr(), height, width, row0)
             bad = status.cpu()      # also orders the staging buffer's reuse after the copy
         if bool(bad.any()):
             f = int(bad.nonzero()[0])
@@ -618,7 +646,8 @@ class FullImagesDataset(Dataset):
                 if by < y_hi and by + ts > y_lo]
         if not mine:
             raise ValueError("no tile of %s covers rows [%d, %d)" % (self.scenes[idx], y_lo, y_hi))
-        out, tiles = d._read_tiles([m[0] for m in mine], y_hi - y_lo, width, row0=y_lo)
+        out, tiles = d._read_tiles([m[0] for m in mine], y_hi - y_lo, width, row0=y_lo,
+                                   clip_rows=True)
         dev = out["target_image"].device
         first = tiles[0]["gfeatures"]
         sample = {"global_features": d._global_features(first, dev),

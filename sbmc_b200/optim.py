@@ -22,6 +22,33 @@ __all__ = ["FusedAdam"]
 _CHUNK = 65536      # SBMC_MT_CHUNK_ELEMS (include/sbmc_b200.h)
 
 
+class _CudaBackend(object):
+    """The launches of a step: libsbmc_b200's kernels on the parameters' CUDA device.
+    (The test-suite swaps in the device sources compiled for the host,
+    tests/native/optim_emul.cpp, to run the Python side without a GPU.)"""
+    device_type = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def scope(self, dev):
+        return th.cuda.device(dev)
+
+    def grad_norm(self, dev, tensors, chunks, nchunks, partial, max_norm, out):
+        _lib.check(self.lib.sbmc_multi_tensor_grad_norm_f32(
+            tensors.data_ptr(), chunks.data_ptr(), nchunks, partial.data_ptr(), max_norm,
+            out.data_ptr(), th.cuda.current_stream(dev).cuda_stream), "grad_norm")
+
+    def adam(self, dev, tensors, chunks, nchunks, coef_ptr, *scalars):
+        _lib.check(self.lib.sbmc_multi_tensor_adam_f32(
+            tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, *scalars,
+            th.cuda.current_stream(dev).cuda_stream), "adam")
+
+
+def _backend():
+    return _CudaBackend()
+
+
 class FusedAdam(th.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
@@ -53,7 +80,7 @@ class FusedAdam(th.optim.Optimizer):
         if closure is not None:
             with th.enable_grad():
                 loss = closure()
-        lib = _lib.load()
+        backend = _backend()
         coef_ptr = None
         groups = []
         everything = []
@@ -63,7 +90,8 @@ class FusedAdam(th.optim.Optimizer):
                 if p.grad is None:
                     continue
                 g = p.grad
-                if not (p.is_cuda and p.dtype == th.float32 and p.is_contiguous()
+                if not (p.device.type == backend.device_type and p.dtype == th.float32
+                        and p.is_contiguous()
                         and g.dtype == th.float32 and g.is_contiguous() and g.device == p.device
                         and not g.is_sparse):
                     raise _lib.SbmcB200Error(
@@ -89,17 +117,15 @@ class FusedAdam(th.optim.Optimizer):
             for r in rows:
                 by_step.setdefault(float(self.state[r[0]]["step"]), []).append(r)
             parts.extend((group, step, part) for step, part in sorted(by_step.items()))
-        with th.cuda.device(dev):
-            stream = th.cuda.current_stream().cuda_stream
+        with backend.scope(dev):
             tables = None
             if max_norm is not None:
                 tables = self._tables(everything, dev)
                 tensors, chunks, nchunks = tables
                 partial = th.empty(max(nchunks, 1), dtype=th.float32, device=dev)
                 self.last_grad_norm = th.empty(2, dtype=th.float32, device=dev)
-                _lib.check(lib.sbmc_multi_tensor_grad_norm_f32(
-                    tensors.data_ptr(), chunks.data_ptr(), nchunks, partial.data_ptr(),
-                    float(max_norm), self.last_grad_norm.data_ptr(), stream), "grad_norm")
+                backend.grad_norm(dev, tensors, chunks, nchunks, partial, float(max_norm),
+                                  self.last_grad_norm)
                 coef_ptr = self.last_grad_norm.data_ptr() + 4
             for group, step, part in parts:
                 beta1, beta2 = group["betas"]
@@ -107,10 +133,8 @@ class FusedAdam(th.optim.Optimizer):
                 if tables is None or len(parts) > 1:
                     tables = self._tables(part, dev)
                 tensors, chunks, nchunks = tables
-                _lib.check(lib.sbmc_multi_tensor_adam_f32(
-                    tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, group["lr"],
-                    beta1, beta2, group["eps"], 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t),
-                    stream), "adam")
+                backend.adam(dev, tensors, chunks, nchunks, coef_ptr, group["lr"], beta1, beta2,
+                             group["eps"], 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t))
                 for r in part:
                     self.state[r[0]]["step"] += 1
         return loss

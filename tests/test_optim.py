@@ -119,11 +119,37 @@ def test_argument_validation_needs_no_gpu():
     assert lib.sbmc_multi_tensor_grad_norm_f32(None, None, 1, None, 1.0, None, None) == -1
 
 
-# ------------------------------------------------------------------ GPU
-@pytest.mark.gpu
+# ------------------------------------------------------------------ FusedAdam, two backends
+class EmulBackend(object):
+    """Stands in for sbmc_b200.optim._CudaBackend: same Python, kernels built for the host."""
+    device_type = "cpu"
+
+    def __init__(self):
+        self.lib = emul()
+
+    def scope(self, dev):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def grad_norm(self, dev, tensors, chunks, nchunks, partial, max_norm, out):
+        self.lib.emul_grad_norm(tensors.data_ptr(), chunks.data_ptr(), nchunks, partial.data_ptr(),
+                                max_norm, out.data_ptr())
+
+    def adam(self, dev, tensors, chunks, nchunks, coef_ptr, *scalars):
+        self.lib.emul_adam(tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, *scalars)
+
+
+@pytest.fixture(params=["host-emulation", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    if request.param == "host-emulation":
+        monkeypatch.setattr(optim, "_backend", EmulBackend)
+        return "cpu"
+    return "cuda"
+
+
 @pytest.mark.parametrize("max_norm", [None, 1000.0, 0.5])
-def test_gpu_fused_adam_matches_torch(max_norm):
-    mine, ref = make_params(0, "cuda"), make_params(0, "cuda")
+def test_fused_adam_matches_torch(max_norm, backend):
+    mine, ref = make_params(0, backend), make_params(0, backend)
     fused = optim.FusedAdam(mine, lr=1e-2)
     opt = th.optim.Adam(ref, lr=1e-2)
     for step in range(1, 6):
@@ -131,7 +157,8 @@ def test_gpu_fused_adam_matches_torch(max_norm):
         set_grads(ref, step, 3.0)
         before = _lib.launch_count()
         fused.step(max_norm=max_norm)
-        assert _lib.launch_count() - before == (3 if max_norm is not None else 1)
+        if backend == "cuda":
+            assert _lib.launch_count() - before == (3 if max_norm is not None else 1)
         if max_norm is not None:
             want = th.nn.utils.clip_grad_norm_(ref, max_norm)
             assert fused.last_grad_norm[0].item() == pytest.approx(want.item(), rel=1e-6)
@@ -143,9 +170,21 @@ def test_gpu_fused_adam_matches_torch(max_norm):
             close(fused.state[p]["exp_avg_sq"], opt.state[q]["exp_avg_sq"], "exp_avg_sq %d" % i,
                   tol)
     # state dicts interchange with torch.optim.Adam
-    other = th.optim.Adam(make_params(0, "cuda"), lr=1e-2)
+    other = th.optim.Adam(make_params(0, backend), lr=1e-2)
     other.load_state_dict(fused.state_dict())
     assert float(other.state[other.param_groups[0]["params"][0]]["step"]) == 5.0
+    # parameters that join later (no gradient so far) start their own step count
+    late = th.nn.Parameter(th.ones(5, device=backend))
+    fused.add_param_group({"params": [late]})
+    set_grads(mine + [late], 9, 1.0)
+    fused.step(max_norm=max_norm)
+    assert float(fused.state[late]["step"]) == 1.0 and float(fused.state[mine[0]]["step"]) == 6.0
+    one = th.nn.Parameter(th.ones(5, device=backend))
+    one.grad = late.grad.clone() if max_norm is None else None
+    if max_norm is None:
+        solo = th.optim.Adam([one], lr=1e-2)
+        solo.step()
+        close(late, one, "late parameter's first step")
 
 
 @pytest.mark.gpu

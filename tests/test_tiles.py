@@ -300,91 +300,189 @@ def test_oracle_reader_matches_reference_fixtures(name):
             check_item(exp, "%s/%d" % (name, i), item, i_diffuse_of(kw))
 
 
-# ------------------------------------------------------------------ device assembly code on the host
-def emul_read(files, kw, height, width, positions=None, force_scalar=False, row0=0):
-    """sbmc_b200.datasets' host planning + the emulated kernels = the product
-    path with the two launches replaced by their host builds."""
-    d = datasets.TilesDataset(DATA, device="cpu", **kw)
-    stage, frames, tiles, raw_bytes = d._plan(files)
-    table = np.array(frames, np.int64).reshape(-1, 4)
-    src = stage.numpy()
-    raw = np.zeros(max(raw_bytes, 16) + 16, np.uint8)
-    off = (-raw.ctypes.data) % 16                       # 16-byte aligned like a device buffer
-    raw = raw[off:off + max(raw_bytes, 16)]
-    status = np.zeros(len(frames), np.int32)
-    vp = ctypes.c_void_p
-    lib = emul()
-    lib.emul_lz4_frames_inflate(src.ctypes.data_as(vp), table.ctypes.data_as(vp), len(frames),
-                                raw.ctypes.data_as(vp), status.ctypes.data_as(vp))
-    assert not status.any(), status
-    ts, spp = d.tile_size, d.spp
-    rows = []
-    for i, t in enumerate(tiles):
-        bx, by = positions[i] if positions else (t["block_x"], t["block_y"])
-        rows.append((t["image_off"], t["samples_off"], bx, by))
-    rows = np.array(rows, np.int64).reshape(-1, 4)
-    nf, nch = len(d.labels), d.pixel_features // 2
-    out = {"image_data": th.zeros(nch, height, width), "image_data_var": th.zeros(nch, height, width),
-           "target_image": th.zeros(3, height, width), "features": th.zeros(spp, nf, height, width),
-           "radiance": th.zeros(spp, 3, height, width), "low_spp": th.zeros(3, height, width)}
-    flags = d._flags() | (0 if force_scalar else 64)
-    rc = lib.emul_tile_assemble_f32(
-        raw.ctypes.data_as(vp), rows.ctypes.data_as(vp), len(tiles),
-        datasets._align(d._sample_frame_bytes()), ts, spp, d.sample_features, d.pixel_features,
-        d.path_depth, flags, out["features"].data_ptr(), out["radiance"].data_ptr(),
-        out["low_spp"].data_ptr(), out["image_data"].data_ptr(), out["image_data_var"].data_ptr(),
-        out["target_image"].data_ptr(), height, width, row0)
-    assert rc == (1 if force_scalar else 4), (rc, lib.emul_last_error())
-    return d, out, tiles
+# ------------------------------------------------------------------ the dataset classes, two backends
+class EmulBackend(object):
+    """Stands in for sbmc_b200.datasets._CudaBackend: the two launches of an item
+    run as the device sources compiled for the host, everything else (file reads,
+    chunk tables, tile tables, allocation, error handling) is the product's own
+    Python code working on CPU tensors."""
+    device = th.device("cpu")
+
+    def __init__(self, device=None):
+        self.lib = emul()
+
+    def scope(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def inflate(self, comp, table, nframes, raw, status):
+        self.lib.emul_lz4_frames_inflate(comp.data_ptr(), table.data_ptr(), nframes, raw.data_ptr(),
+                                         status.data_ptr())
+
+    def assemble(self, *args):
+        rc = self.lib.emul_tile_assemble_f32(*args)
+        if rc < 0:
+            raise RuntimeError(self.lib.emul_last_error().decode())
+        self.last_vec = rc
 
 
-@pytest.mark.parametrize("force_scalar", [False, True], ids=["vec4", "scalar"])
-@pytest.mark.parametrize("name", sorted(SBMC_CONFIGS))
-def test_emulated_kernels_match_reference_fixtures(name, force_scalar):
-    full, listed, kw = SBMC_CONFIGS[name]
+BACKENDS = ["host-emulation", pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def backend(request, monkeypatch):
+    """"host-emulation": product Python + device code built for the host (runs
+    everywhere); "gpu": the product as shipped."""
+    if request.param == "host-emulation":
+        monkeypatch.setattr(datasets, "_backend", EmulBackend)
+    return request.param
+
+
+def launches():
+    return _lib.launch_count()
+
+
+ALL_CONFIGS = sorted(SBMC_CONFIGS) + ["tiles_kpcn", "full_kpcn"]
+
+
+def config_of(name):
+    if name in SBMC_CONFIGS:
+        return SBMC_CONFIGS[name]
+    full = name.startswith("full")
+    return full, False, (dict(mode="kpcn", spp=2) if full else dict(mode="kpcn"))
+
+
+@pytest.mark.parametrize("scalar", [False, True], ids=["vec4", "scalar"])
+@pytest.mark.parametrize("name", ALL_CONFIGS)
+def test_datasets_match_reference_fixtures(name, scalar, backend, monkeypatch):
+    """Every item of every configuration against what the reference's own
+    sbmc/datasets.py produced for the same files."""
+    if scalar:
+        if name.endswith("kpcn"):
+            pytest.skip("same kernels as the sbmc configurations")
+        monkeypatch.setattr(datasets, "_F_ALIGNED", 0)        # forces the 1-pixel kernel
     exp = expected()
-    files = fixture_files(listed)
-    if full:
-        for s in range(2):
-            d, out, tiles = emul_read(files[4 * s:4 * s + 4], kw, 16, 16, force_scalar=force_scalar)
-            out["spp"] = np.full((1, 16, 16), d.spp, np.int32)
-            out["global_features"] = d._global_features(tiles[0]["gfeatures"], "cpu")
-            out["scene_radius"] = tiles[0]["gfeatures"]["scene_radius"]
-            check_item(exp, "%s/%d" % (name, s), out, i_diffuse_of(kw))
-    else:
-        for i, f in enumerate(files):
-            d, out, tiles = emul_read([f], kw, 8, 8, positions=[(0, 0)], force_scalar=force_scalar)
-            out.update(block_x=tiles[0]["block_x"], block_y=tiles[0]["block_y"],
-                       spp=np.full((1, 1, 1), d.spp, np.int32),
-                       scene_radius=tiles[0]["gfeatures"]["scene_radius"],
-                       global_features=d._global_features(tiles[0]["gfeatures"], "cpu"))
-            check_item(exp, "%s/%d" % (name, i), out, i_diffuse_of(kw))
+    full, listed, kw = config_of(name)
+    path = os.path.join(DATA, "list.txt") if listed else DATA
+    d = (datasets.FullImagesDataset if full else datasets.TilesDataset)(path, **kw)
+    assert len(d) == int(exp[name + "/len"])
+    before = launches()
+    for i in range(len(d)):
+        item = d[i]
+        if backend == "gpu":
+            assert all(v.is_cuda for v in item.values() if isinstance(v, th.Tensor))
+            assert _lib.last_path() == (2 if scalar else 1)
+        item = {k: v for k, v in item.items() if k != "path"}
+        check_item(exp, "%s/%d" % (name, i), item, i_diffuse_of(kw))
+    if backend == "gpu":
+        assert launches() >= before + 2 * len(d)          # our kernels did the work
 
 
-@pytest.mark.parametrize("y_lo,y_hi", [(0, 16), (0, 5), (3, 11), (8, 16), (12, 13)])
-def test_emulated_row_band_equals_rows_of_the_full_image(y_lo, y_hi):
-    """Row-sharded reading: assembling rows [y_lo, y_hi) from the tiles that
-    intersect them gives exactly those rows of the whole image."""
-    files = fixture_files(False)[:4]
-    _, whole, _ = emul_read(files, {}, 16, 16)
-    full = datasets.FullImagesDataset(DATA, device="cpu")
-    mine = [f for f, bx, by in full.tile_positions(0) if by < y_hi and by + 8 > y_lo]
-    assert set(mine) <= set(files) and (len(mine) == 2) == (y_hi <= 8 or y_lo >= 8)
-    _, band, _ = emul_read(mine, {}, y_hi - y_lo, 16, row0=y_lo)
-    for k, v in whole.items():
-        assert th.equal(band[k], v[..., y_lo:y_hi, :]), k
+@pytest.mark.parametrize("ts,tiles_x,tiles_y,spp", [(32, 3, 2, 4), (6, 2, 3, 2), (128, 1, 1, 8)])
+def test_full_image_matches_oracle_on_larger_tiles(tmp_path, ts, tiles_x, tiles_y, spp, backend):
+    """Bigger tiles (multi-block linked frames at ts = 128), a tile size that is not
+    a multiple of 4 (scalar kernel), several tiles pasted by one launch."""
+    if backend == "host-emulation" and ts == 128:
+        spp = 2                                            # keep the CPU suite quick
+    rng = np.random.default_rng(ts)
+    compress = tile_io.compress_frame if tile_io.liblz4() else tile_io.stored_frame
+    tile_io.write_scene(str(tmp_path), "scene", rng, ts, tiles_x, tiles_y, spp, quantize=1.0 / 64,
+                        compress=compress)
+    d = datasets.FullImagesDataset(str(tmp_path))
+    item = d[0]
+    files = sorted(os.listdir(tmp_path / "scene"))
+    ref = tiles_ref.read_image([open(tmp_path / "scene" / f, "rb").read() for f in files])
+    if backend == "gpu":
+        assert _lib.last_path() == (1 if ts % 4 == 0 else 2)
+    for k, v in ref.items():
+        if not isinstance(v, np.ndarray):
+            continue
+        got = item[k].cpu().numpy()
+        assert got.shape == v.shape and got.dtype == v.dtype, k
+        if k == "features":
+            i = 5
+            rest = lambda a: np.concatenate([a[:, :i], a[:, i + 6:]], 1)  # noqa: E731
+            assert np.array_equal(rest(got).view(np.int32), rest(v).view(np.int32))
+            tol = LOG_RTOL * np.maximum(np.abs(v[:, i:i + 6]), 1e-3)
+            assert (np.abs(got[:, i:i + 6].astype(np.float64) - v[:, i:i + 6]) <= tol).all()
+        else:
+            assert np.array_equal(got.view(np.int32), v.view(np.int32)), k
+    # a tiles-dataset item of the same scene agrees with its region of the full image
+    t = d.tiles_dset[len(d.tiles_dset) - 1]
+    by, bx = t["block_y"], t["block_x"]
+    assert th.equal(t["radiance"], item["radiance"][..., by:by + ts, bx:bx + ts])
+    assert th.equal(t["features"], item["features"][..., by:by + ts, bx:bx + ts])
 
 
-def test_emulated_batched_layout_equals_single_tiles():
-    """TilesDataset.__getitems__ stacks the batch's tiles along rows of one scratch
-    image: each slice must equal the tile assembled alone."""
-    files = fixture_files(False)[2:7]
-    _, stacked, _ = emul_read(files, dict(spp=2), 8 * len(files), 8,
-                              positions=[(0, 8 * i) for i in range(len(files))])
-    for i, f in enumerate(files):
-        _, one, _ = emul_read([f], dict(spp=2), 8, 8, positions=[(0, 0)])
+def test_row_bands_tile_the_full_image(backend):
+    """Row-sharded reading: what each rank of a multi-GPU job reads (BandPlan rows +
+    halo) equals those rows of the whole image; only intersecting tiles are read."""
+    from sbmc_b200.sharding import BandPlan
+    d = datasets.FullImagesDataset(DATA)
+    whole = d[1]
+    plan = BandPlan(16, 2, 5, align=4)
+    bands = [(plan.y0[r] - plan.halo_top(r), plan.y1[r] + plan.halo_bot(r)) for r in range(2)]
+    for lo, hi in bands + [(0, 5), (3, 11), (8, 16), (12, 13)]:
+        mine = [f for f, bx, by in d.tile_positions(1) if by < hi and by + 8 > lo]
+        assert (len(mine) == 2) == (hi <= 8 or lo >= 8)
+        band = d.read_rows(1, lo, hi)
+        assert set(band) == set(whole)
+        for k, v in whole.items():
+            if isinstance(v, th.Tensor) and v.dim() >= 3 and v.shape[-1] == 16:
+                assert th.equal(band[k], v[..., lo:hi, :]), (k, lo, hi)
+    with pytest.raises(ValueError):
+        d.read_rows(0, 4, 4)
+    with pytest.raises(ValueError):
+        datasets.FullImagesDataset(DATA, mode="kpcn").read_rows(0, 0, 8)
+
+
+def test_batched_fetch_equals_single_items(backend):
+    """DataLoader batches go through TilesDataset.__getitems__ (one pair of
+    launches per batch) and must equal the items fetched one by one."""
+    from torch.utils.data import DataLoader
+    d = datasets.TilesDataset(DATA, spp=2)
+    before = launches()
+    batch = next(iter(DataLoader(d, batch_size=5, shuffle=False, num_workers=0)))
+    if backend == "gpu":
+        assert launches() == before + 2
+    assert batch["features"].shape == (5, 2, 93, 8, 8) and batch["spp"].shape == (5, 1, 1, 1)
+    for i in range(5):
+        one = d[i]
         for k, v in one.items():
-            assert th.equal(stacked[k][..., 8 * i:8 * i + 8, :], v), (k, i)
+            if isinstance(v, th.Tensor):
+                assert th.equal(batch[k][i], v), (k, i)
+            elif isinstance(v, str):
+                assert batch[k][i] == v
+            else:
+                assert batch[k][i].item() == pytest.approx(v)
+
+
+def test_corrupt_tile_raises_like_the_reference(tmp_path, backend):
+    src = fixture_files(False)[0]
+    folder = tmp_path / "scene"
+    folder.mkdir()
+    blob = bytearray(open(src, "rb").read())
+    (n0,) = struct.unpack_from("<i", blob, 60)
+    blob[64 + n0 + 4:64 + n0 + 8] = b"\0\0\0\0"          # destroy the first sample frame's magic
+    (folder / "bad.bin").write_bytes(bytes(blob))
+    d = datasets.TilesDataset(str(tmp_path))
+    with pytest.raises(RuntimeError, match="LZ4 frame 1"):
+        d[0]
+    with pytest.raises(ValueError, match="does not fit"):
+        datasets.TilesDataset(DATA)._read_tiles([fixture_files(False)[3]], 8, 8)   # tile at (8, 8)
+
+
+def test_zero_samples_and_multi_sample_count(backend):
+    d0 = datasets.TilesDataset(DATA, spp=0)
+    item = d0[0]
+    assert "features" not in item and "radiance" not in item
+    assert item["low_spp"].dtype == th.float64 and not item["low_spp"].any()
+    assert item["target_image"].shape == (3, 8, 8)
+    multi = datasets.MultiSampleCountDataset(DATA, spp=3)
+    exp = expected()
+    got = [int(multi[i]["spp"].reshape(-1)[0]) for i in range(len(multi))]
+    assert got == exp["multi/spp_of_items"].tolist()
+    assert multi[0]["features"].shape[0] == 2 and multi[len(multi) - 1]["features"].shape[0] == 3
 
 
 # ------------------------------------------------------------------ host logic of sbmc_b200.datasets
@@ -586,116 +684,6 @@ def test_gpu_inflater_error_statuses_match_the_emulation():
     outs, got = _gpu_inflate([c[0] for c in cases], [c[1] for c in cases])
     assert list(got) == list(want) == expect
     assert outs[4] == raw + raw and outs[5] == raw
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(SBMC_CONFIGS) + ["tiles_kpcn", "full_kpcn"])
-def test_gpu_datasets_match_reference_fixtures(name):
-    exp = expected()
-    if name in SBMC_CONFIGS:
-        full, listed, kw = SBMC_CONFIGS[name]
-    else:
-        full, listed, kw = name.startswith("full"), False, dict(mode="kpcn")
-        if full:
-            kw["spp"] = 2
-    path = os.path.join(DATA, "list.txt") if listed else DATA
-    d = (datasets.FullImagesDataset if full else datasets.TilesDataset)(path, **kw)
-    assert len(d) == int(exp[name + "/len"])
-    before = _lib.launch_count()
-    for i in range(len(d)):
-        item = d[i]
-        assert all(v.is_cuda for v in item.values() if isinstance(v, th.Tensor))
-        item = {k: v for k, v in item.items() if k != "path"}
-        check_item(exp, "%s/%d" % (name, i), item, i_diffuse_of(kw))
-    assert _lib.launch_count() >= before + 2 * len(d)          # our kernels did the work
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("ts,tiles_x,tiles_y,spp", [(32, 3, 2, 4), (6, 2, 3, 2), (128, 1, 1, 8)])
-def test_gpu_full_image_matches_oracle_on_larger_tiles(tmp_path, ts, tiles_x, tiles_y, spp):
-    """Bigger tiles (multi-block linked frames at ts = 128), a tile size that is not
-    a multiple of 4 (scalar kernel), several tiles pasted by one launch."""
-    rng = np.random.default_rng(ts)
-    compress = tile_io.compress_frame if tile_io.liblz4() else tile_io.stored_frame
-    tile_io.write_scene(str(tmp_path), "scene", rng, ts, tiles_x, tiles_y, spp, quantize=1.0 / 64,
-                        compress=compress)
-    d = datasets.FullImagesDataset(str(tmp_path))
-    item = d[0]
-    files = sorted(os.listdir(tmp_path / "scene"))
-    ref = tiles_ref.read_image([open(tmp_path / "scene" / f, "rb").read() for f in files])
-    assert _lib.last_path() == (1 if ts % 4 == 0 else 2)
-    for k, v in ref.items():
-        if not isinstance(v, np.ndarray):
-            continue
-        got = item[k].cpu().numpy()
-        assert got.shape == v.shape and got.dtype == v.dtype, k
-        if k == "features":
-            i = 5
-            rest = lambda a: np.concatenate([a[:, :i], a[:, i + 6:]], 1)  # noqa: E731
-            assert np.array_equal(rest(got).view(np.int32), rest(v).view(np.int32))
-            tol = LOG_RTOL * np.maximum(np.abs(v[:, i:i + 6]), 1e-3)
-            assert (np.abs(got[:, i:i + 6].astype(np.float64) - v[:, i:i + 6]) <= tol).all()
-        else:
-            assert np.array_equal(got.view(np.int32), v.view(np.int32)), k
-    # a tiles-dataset item of the same scene agrees with its region of the full image
-    t = d.tiles_dset[1]
-    by, bx = t["block_y"], t["block_x"]
-    assert th.equal(t["radiance"], item["radiance"][..., by:by + ts, bx:bx + ts])
-    assert th.equal(t["features"], item["features"][..., by:by + ts, bx:bx + ts])
-
-
-@pytest.mark.gpu
-def test_gpu_row_bands_tile_the_full_image():
-    """What each rank of a row-sharded job reads (BandPlan rows + halo)."""
-    from sbmc_b200.sharding import BandPlan
-    d = datasets.FullImagesDataset(DATA)
-    whole = d[1]
-    plan = BandPlan(16, 2, 5, align=4)
-    for rank in range(2):
-        lo = plan.y0[rank] - plan.halo_top(rank)
-        hi = plan.y1[rank] + plan.halo_bot(rank)
-        band = d.read_rows(1, lo, hi)
-        assert set(band) == set(whole)
-        for k, v in whole.items():
-            if isinstance(v, th.Tensor) and v.dim() >= 3 and v.shape[-1] == 16:
-                assert th.equal(band[k], v[..., lo:hi, :]), k
-    with pytest.raises(ValueError):
-        d.read_rows(0, 4, 4)
-
-
-@pytest.mark.gpu
-def test_gpu_batched_fetch_equals_single_items():
-    """DataLoader batches go through TilesDataset.__getitems__ (one pair of
-    launches per batch) and must equal the items fetched one by one."""
-    from torch.utils.data import DataLoader
-    d = datasets.TilesDataset(DATA, spp=2)
-    before = _lib.launch_count()
-    batch = next(iter(DataLoader(d, batch_size=5, shuffle=False, num_workers=0)))
-    assert _lib.launch_count() == before + 2
-    assert batch["features"].shape == (5, 2, 93, 8, 8) and batch["spp"].shape == (5, 1, 1, 1)
-    for i in range(5):
-        one = d[i]
-        for k, v in one.items():
-            if isinstance(v, th.Tensor):
-                assert th.equal(batch[k][i], v), (k, i)
-            elif isinstance(v, str):
-                assert batch[k][i] == v
-            else:
-                assert batch[k][i].item() == pytest.approx(v)
-
-
-@pytest.mark.gpu
-def test_gpu_corrupt_tile_raises_like_the_reference(tmp_path):
-    src = fixture_files(False)[0]
-    folder = tmp_path / "scene"
-    folder.mkdir()
-    blob = bytearray(open(src, "rb").read())
-    (n0,) = struct.unpack_from("<i", blob, 60)
-    blob[64 + n0 + 4:64 + n0 + 8] = b"\0\0\0\0"          # destroy the first sample frame's magic
-    (folder / "bad.bin").write_bytes(bytes(blob))
-    d = datasets.TilesDataset(str(tmp_path))
-    with pytest.raises(RuntimeError, match="LZ4 frame 1"):
-        d[0]
 
 
 @pytest.mark.gpu

@@ -101,12 +101,22 @@ def build_model(data, meta, fast=False):
     return model
 
 
+def _device():
+    if not th.cuda.is_available():
+        raise RuntimeError("sbmc_b200 runs on a CUDA device only (no CPU path)")
+    return "cuda"
+
+
+def _sync(device):
+    if device == "cuda":
+        th.cuda.synchronize()
+
+
 def main(args):
     start = time.time()
     if not os.path.exists(args.input):
         raise ValueError("input {} does not exist".format(args.input))
-    if not th.cuda.is_available():
-        raise RuntimeError("sbmc_b200 runs on a CUDA device only (no CPU path)")
+    device = _device()
     # the dataset wants a root of scene folders; `input` is one scene (denoise.py:101-104)
     data_root = os.path.abspath(args.input)
     tmpdir = tempfile.mkdtemp()
@@ -122,17 +132,17 @@ def main(args):
     kpcn_mode = bool(meta.get("kpcn_mode"))
     model = build_model(data, meta, fast=args.fast)
     model.train(False)
-    model.cuda()
+    model.to(device)
     _, loaded = _compat.Checkpointer(args.checkpoint, model, None).load_latest()
     LOG.info("Loading latest checkpoint %s", "failed" if loaded is None else "success")
     LOG.info("setup time %.1f ms", (time.time() - start) * 1000)
 
     loader = DataLoader(data, batch_size=1, shuffle=False, num_workers=0)
     for batch in loader:
-        th.cuda.synchronize()
+        _sync(device)
         start = time.time()
         out = denoise_batch(model, batch, kpcn_mode, int(args.tile_size), int(args.tile_pad))
-        th.cuda.synchronize()
+        _sync(device)
         LOG.info("    denoising time %.1f ms", (time.time() - start) * 1000)
         image = out[0].float().cpu().numpy().transpose([1, 2, 0])
         outdir = os.path.dirname(os.path.abspath(args.output))

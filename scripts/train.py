@@ -25,11 +25,16 @@ from sbmc_b200 import _compat, datasets, interfaces, models  # noqa: E402
 LOG = _compat.get_logger(__name__)
 
 
+def _device():
+    if not th.cuda.is_available():
+        raise RuntimeError("sbmc_b200 runs on a CUDA device only (no CPU path)")
+    return "cuda"
+
+
 def main(args):
     np.random.seed(0)
     th.manual_seed(0)
-    if not th.cuda.is_available():
-        raise RuntimeError("sbmc_b200 runs on a CUDA device only (no CPU path)")
+    device = _device()
     data_args = dict(spp=args.spp,
                      mode=datasets.TilesDataset.KPCN_MODE if args.kpcn_mode
                      else datasets.TilesDataset.SBMC_MODE,
@@ -62,7 +67,7 @@ def main(args):
 
     meta = dict(model_params=model_params, kpcn_mode=args.kpcn_mode, data_params=data_args)
     LOG.info("Model configuration: %s", model_params)
-    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=True,
+    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=device == "cuda",
                                                         fused_optimizer=args.fused_optimizer)
     checkpointer = _compat.Checkpointer(args.checkpoint_dir, model, meta=meta,
                                         optimizers=interface.optimizer)

@@ -171,7 +171,7 @@ def test_script_parsers_keep_the_reference_options():
         8, 21, False, False, True, True, 1e-4)
 
 
-# ------------------------------------------------------------------ GPU: end to end
+# ------------------------------------------------------------------ end to end, two backends
 def _scene(tmp_path, ts=16, nx=3, ny=3, spp=2):
     rng = np.random.default_rng(5)
     compress = tile_io.compress_frame if tile_io.liblz4() else tile_io.stored_frame
@@ -180,20 +180,44 @@ def _scene(tmp_path, ts=16, nx=3, ny=3, spp=2):
     return str(tmp_path / "data")
 
 
-@pytest.mark.gpu
-def test_gpu_train_then_denoise_scripts(tmp_path):
+@pytest.fixture(params=["host-emulation", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    """"gpu": the scripts as shipped.  "host-emulation": the same Python with the
+    tile kernels built for the host (tests/test_tiles.py), the optimizer kernels
+    likewise (tests/test_optim.py) and the two custom ops stood in for by the
+    oracle, on CPU tensors -- checks the scripts' own logic without a GPU."""
+    if request.param == "host-emulation":
+        import sbmc_b200.functions as funcs
+        from sbmc_b200 import datasets, optim
+        from tests import kats
+        from tests.test_optim import EmulBackend as OptimEmul
+        from tests.test_tiles import EmulBackend as TilesEmul
+        KW, S2G = kats.oracle_functions()
+        monkeypatch.setattr(funcs, "KernelWeighting", KW)
+        monkeypatch.setattr(funcs, "Scatter2Gather", S2G)
+        monkeypatch.setattr(datasets, "_backend", TilesEmul)
+        monkeypatch.setattr(optim, "_backend", OptimEmul)
+    return request.param
+
+
+@pytest.mark.parametrize("fused_optimizer", [False, True], ids=["adam", "fused-adam"])
+def test_train_then_denoise_scripts(tmp_path, backend, fused_optimizer, monkeypatch):
     root = _scene(tmp_path)
     train = load_script("train")
+    denoise = load_script("denoise")
+    if backend == "host-emulation":
+        monkeypatch.setattr(train, "_device", lambda: "cpu")
+        monkeypatch.setattr(denoise, "_device", lambda: "cpu")
     ckpt = str(tmp_path / "ckpt")
     args = train.parser().parse_args(
         ["--data", root, "--checkpoint_dir", ckpt, "--constant_spp", "--spp", "2", "--bs", "3",
-         "--ksize", "3", "--num_epochs", "1", "--max_steps", "2", "--log_every", "1"])
+         "--ksize", "3", "--num_epochs", "1", "--max_steps", "2", "--log_every", "1"]
+        + (["--fused_optimizer"] if fused_optimizer else []))
     train.main(args)
     assert "training_end.pth" in os.listdir(ckpt)
     meta = _compat.Checkpointer.load_meta(ckpt)
     assert meta["model_params"]["ksize"] == 3 and meta["data_params"]["spp"] == 2
 
-    denoise = load_script("denoise")
     outs = {}
     for name, extra in (("whole", []), ("tiled", ["--tile_size", "32", "--tile_pad", "8"])):
         out = str(tmp_path / ("%s.exr" % name))

@@ -162,3 +162,48 @@ def test_tiled_model_inference_gloo(world):
         assert p.exitcode == 0
     for rank, res in results:
         assert all(res.values()), (rank, res)
+
+
+def _reader_worker(rank, world, port, q):
+    """Row-sharded reading of a scene (tile files -> each rank's band, no exchange)
+    followed by the final gather: every rank ends with the whole image.  The two
+    launches of the reader run as the device code built for the host."""
+    from sbmc_b200 import datasets
+    from tests.test_tiles import DATA, EmulBackend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        datasets._backend = EmulBackend
+        d = datasets.FullImagesDataset(DATA, spp=2)
+        plan = sharding.BandPlan(d.tiles_dset.image_height, world, 3)
+        res = {}
+        lo, hi = plan.y0[rank], plan.y1[rank]
+        band = d.read_rows(1, lo, hi)
+        whole = d[1]
+        for key, dim in (("features", 2), ("radiance", 2), ("low_spp", 1), ("target_image", 1)):
+            full = sharding.gather_bands(plan, rank, band[key], dim)
+            res[key] = th.equal(full, whole[key])
+        # with the K x K halo the band is what the sharded model consumes
+        top, bot = plan.halo_top(rank), plan.halo_bot(rank)
+        ext = d.read_rows(1, lo - top, hi + bot)["features"]
+        res["halo"] = th.equal(ext, whole["features"][..., lo - top:hi + bot, :])
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_reader_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reader_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in results:
+        assert all(res.values()), (rank, res)

@@ -161,3 +161,19 @@ def test_reference_functions_bind_to_the_drop_in(monkeypatch):
         ref.KernelWeighting.apply(th.zeros(2, 3, 8, 8), th.zeros(2, 5, 5, 8, 8))
     with pytest.raises(RuntimeError, match="no CPU compute path"):
         ref.Scatter2Gather.apply(th.zeros(2, 5, 5, 8, 8))
+
+
+def test_package_exports_the_reference_top_level_names():
+    """sbmc/__init__.py re-exports its datasets, models and interface: the same
+    names resolve on this package."""
+    import sbmc_b200 as sbmc
+    from sbmc_b200 import datasets, interfaces, models
+    assert sbmc.TilesDataset is datasets.TilesDataset
+    assert sbmc.FullImagesDataset is datasets.FullImagesDataset
+    assert sbmc.MultiSampleCountDataset is datasets.MultiSampleCountDataset
+    assert sbmc.Multisteps is models.Multisteps and sbmc.KPCN is models.KPCN
+    assert sbmc.SampleBasedDenoiserInterface is interfaces.SampleBasedDenoiserInterface
+    assert sbmc.TilesDataset.KPCN_MODE == "kpcn" and sbmc.TilesDataset.SBMC_MODE == "sbmc"
+    assert "Multisteps" in dir(sbmc)
+    with pytest.raises(AttributeError):
+        sbmc.DenoisingDisplayCallback

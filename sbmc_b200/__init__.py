@@ -13,11 +13,11 @@ __version__ = "0.1.0"
 # The names the reference package exports at top level (sbmc/__init__.py:19-23:
 # `from .datasets import *`, `.models`, `.interfaces`), resolved on first use so
 # that `import sbmc_b200 as sbmc; sbmc.Multisteps(...)` reads like the
-# reference's scripts.  (`DenoisingDisplayCallback` is Visdom tooling: not built.)
+# reference's scripts.
 _EXPORTS = {
     "TilesDataset": "datasets", "FullImagesDataset": "datasets",
     "MultiSampleCountDataset": "datasets", "Multisteps": "models", "KPCN": "models",
-    "SampleBasedDenoiserInterface": "interfaces",
+    "SampleBasedDenoiserInterface": "interfaces", "DenoisingDisplayCallback": "callbacks",
 }
 
 

@@ -20,7 +20,7 @@ from torch.utils.data import DataLoader
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from sbmc_b200 import _compat, datasets, interfaces, models  # noqa: E402
+from sbmc_b200 import _compat, callbacks, datasets, interfaces, models  # noqa: E402
 
 LOG = _compat.get_logger(__name__)
 
@@ -76,6 +76,9 @@ def main(args):
     trainer = _compat.Trainer(interface)
     trainer.add_callback(_compat.LoggingCallback(["loss", "rmse"], frequency=args.log_every))
     trainer.add_callback(_compat.CheckpointingCallback(checkpointer))
+    if args.display_every > 0:      # the reference shows this gallery in Visdom (train.py:116-118)
+        trainer.add_callback(callbacks.DenoisingDisplayCallback(
+            frequency=args.display_every, out_dir=os.path.join(args.checkpoint_dir, "display")))
     LOG.info("Training started, 'Ctrl+C' to abort.")
     trainer.train(loader, num_epochs=args.num_epochs, val_dataloader=val_loader,
                   max_steps=args.max_steps)
@@ -92,6 +95,8 @@ def parser():
     p.add_argument("--num_epochs", type=int)
     p.add_argument("--max_steps", type=int, help="stop after this many steps (extra).")
     p.add_argument("--log_every", type=int, default=50)
+    p.add_argument("--display_every", type=int, default=0,
+                   help="write a low-spp / output / target / difference gallery every N steps.")
     p.add_argument("--fused_optimizer", action="store_true",
                    help="clip + Adam over all tensors in three launches (extra).")
     p.add_argument("--spp", type=int, default=8, help="Max number of samples per pixel.")

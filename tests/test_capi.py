@@ -175,5 +175,6 @@ def test_package_exports_the_reference_top_level_names():
     assert sbmc.SampleBasedDenoiserInterface is interfaces.SampleBasedDenoiserInterface
     assert sbmc.TilesDataset.KPCN_MODE == "kpcn" and sbmc.TilesDataset.SBMC_MODE == "sbmc"
     assert "Multisteps" in dir(sbmc)
+    assert sbmc.DenoisingDisplayCallback.__module__ == "sbmc_b200.callbacks"
     with pytest.raises(AttributeError):
-        sbmc.DenoisingDisplayCallback
+        sbmc.NoSuchName

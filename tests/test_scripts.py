@@ -161,6 +161,26 @@ def test_exr_and_png_writers(tmp_path):
     assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(9, 4, 3), rgb)
 
 
+def test_display_callback_gallery_follows_the_reference(tmp_path):
+    from sbmc_b200 import callbacks
+    g = th.Generator().manual_seed(0)
+    batch = {"low_spp": 3 * th.rand(2, 3, 10, 12, generator=g) - 0.5,
+             "target_image": 3 * th.rand(2, 3, 10, 12, generator=g),
+             "spp": th.full((2, 1, 1, 1), 4, dtype=th.int32)}
+    fwd = {"radiance": 3 * th.rand(2, 3, 8, 10, generator=g)}
+    cb = callbacks.DenoisingDisplayCallback(frequency=2, out_dir=str(tmp_path))
+    img = cb.visualized_image(batch, fwd)
+    assert img.shape == (2, 3, 32, 10) and img.min() >= 0 and img.max() <= 1
+    out, tgt = fwd["radiance"], batch["target_image"][..., 1:-1, 1:-1]
+    want = th.cat([batch["low_spp"][..., 1:-1, 1:-1], out, tgt, (out - tgt).abs()], -2).clamp(min=0)
+    want = (want / (1 + want)).pow(1 / 2.2).clamp(0, 1)      # sbmc/callbacks.py:49-57
+    assert th.allclose(img, want)
+    assert cb.caption(batch, fwd) == "vertically: 4spp, ours, target, difference"
+    assert cb.batch_end(batch, fwd, {}) is None
+    path = cb.batch_end(batch, fwd, {})
+    assert path.endswith("images_000002.png") and os.path.getsize(path) > 100
+
+
 def test_script_parsers_keep_the_reference_options():
     d = load_script("denoise").parser().parse_args(
         ["--input", "i", "--checkpoint", "c", "--output", "o.exr", "--spp", "4"])
@@ -211,10 +231,12 @@ def test_train_then_denoise_scripts(tmp_path, backend, fused_optimizer, monkeypa
     ckpt = str(tmp_path / "ckpt")
     args = train.parser().parse_args(
         ["--data", root, "--checkpoint_dir", ckpt, "--constant_spp", "--spp", "2", "--bs", "3",
-         "--ksize", "3", "--num_epochs", "1", "--max_steps", "2", "--log_every", "1"]
+         "--ksize", "3", "--num_epochs", "1", "--max_steps", "2", "--log_every", "1",
+         "--display_every", "2"]
         + (["--fused_optimizer"] if fused_optimizer else []))
     train.main(args)
     assert "training_end.pth" in os.listdir(ckpt)
+    assert os.listdir(os.path.join(ckpt, "display")) == ["images_000002.png"]
     meta = _compat.Checkpointer.load_meta(ckpt)
     assert meta["model_params"]["ksize"] == 3 and meta["data_params"]["spp"] == 2
 

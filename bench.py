@@ -52,6 +52,10 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="kernel_weighting", choices=["kernel_weighting", "tiles"],
+                   help="kernel_weighting: the headline metric (default).  tiles: the tile "
+                        "reader side benchmark (benchmarks/tiles_bench.py) with its CPU leg")
+    p.add_argument("--tile-size", type=int, default=80)
     p.add_argument("--b", type=int, default=4)
     p.add_argument("--spp", type=int, default=8)
     p.add_argument("--h", type=int, default=720)
@@ -414,9 +418,30 @@ def run_e2e(a, th, halide_ops, dev, world, dist):
                    "(sbmc_kernel_weighting_{fwd,bwd}_host_f32), pinned host tensors"}
 
 
+def run_tiles(a):
+    """Side benchmark of the tile reader.  The CPU leg (the reference's reader
+    restated: oracle/tiles_ref.py + oracle/lz4_oracle.c, single thread) lives here
+    because bench.py is the one benchmark that may execute oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import tiles_bench
+
+    def cpu_seconds_per_tile(bufs):
+        from oracle import tiles_ref
+        t0 = time.perf_counter()
+        for b in bufs:
+            tiles_ref.read_tile(b)
+        return (time.perf_counter() - t0) / len(bufs)
+
+    argv = ["--w", str(a.w), "--h", str(a.h), "--ts", str(a.tile_size), "--spp", str(a.spp),
+            "--steps", str(min(a.steps, 5))]
+    tiles_bench.main(argv, None if a.no_cpu_baseline else cpu_seconds_per_tile)
+
+
 def main():
     a = parse_args()
-    if a.impl == "reference":
+    if a.workload == "tiles":
+        run_tiles(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

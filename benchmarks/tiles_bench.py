@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the tile reader (sbmc_b200.datasets).
 
-  python benchmarks/tiles_bench.py [--w 1280 --h 720 --ts 80 --spp 8 --steps 5]
+  python bench.py --workload tiles [--w 1280 --h 720 --tile-size 80 --spp 8 --steps 5]
+  python benchmarks/tiles_bench.py [...]        # the same without the CPU leg
 
 Writes one synthetic scene (tiles in the reference renderer's format, real LZ4
 frames) to a scratch folder and times `FullImagesDataset[0]`:
@@ -10,7 +11,8 @@ frames) to a scratch folder and times `FullImagesDataset[0]`:
     clock around the item plus the two kernels' device times and their
     algorithmic bytes (inflate: compressed in + inflated out; assembly: inflated
     in + tensors out);
-  * "cpu" (the reference algorithm restated, oracle/tiles_ref.py + lz4_oracle.c,
+  * "cpu_baseline" (only through bench.py, the one benchmark allowed to execute
+    oracle/: the reference algorithm restated, oracle/tiles_ref.py + lz4_oracle.c,
     single thread like the reference's DataLoader with num_workers=0) on a bounded
     number of tiles, scaled to the image.
 Prints one JSON line.  Numbers are only meaningful on the GPU box.
@@ -31,7 +33,8 @@ from sbmc_b200 import _lib, datasets
 from tests import tile_io
 
 
-def main():
+def main(argv=None, cpu_baseline=None):
+    """cpu_baseline(tile file contents) -> seconds per tile (supplied by bench.py)."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--w", type=int, default=1280)
     ap.add_argument("--h", type=int, default=720)
@@ -41,7 +44,7 @@ def main():
     ap.add_argument("--cpu_tiles", type=int, default=4)
     ap.add_argument("--quantize", type=float, default=1.0 / 256,
                     help="value grid of the synthetic floats (controls the compression ratio)")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     assert a.w % a.ts == 0 and a.h % a.ts == 0
     root = tempfile.mkdtemp(prefix="sbmc_tiles_")
     try:
@@ -85,15 +88,13 @@ def main():
                 line["gpu"]["kernels_GBps"] = (
                     (file_bytes + 2 * inflated + out_bytes) / (kern[0] / a.steps * 1e-3) / 1e9)
 
-        from oracle import tiles_ref
-        n = min(a.cpu_tiles, len(files))
-        bufs = [open(os.path.join(root, "scene", f), "rb").read() for f in files[:n]]
-        t0 = time.perf_counter()
-        for b in bufs:
-            tiles_ref.read_tile(b)
-        cpu = (time.perf_counter() - t0) / n * len(files)
-        line["cpu_baseline"] = {"value": samples / cpu / 1e6, "unit": "Msamples/s", "cores": 1,
-                                "kind": "port", "sample": "%d of %d tiles, scaled" % (n, len(files))}
+        if cpu_baseline is not None:
+            n = min(a.cpu_tiles, len(files))
+            bufs = [open(os.path.join(root, "scene", f), "rb").read() for f in files[:n]]
+            cpu = cpu_baseline(bufs) * len(files)
+            line["cpu_baseline"] = {"value": samples / cpu / 1e6, "unit": "Msamples/s", "cores": 1,
+                                    "kind": "port",
+                                    "sample": "%d of %d tiles, scaled" % (n, len(files))}
         print(json.dumps(line))
     finally:
         shutil.rmtree(root)

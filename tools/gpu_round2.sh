@@ -12,7 +12,7 @@ timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_tiles.
   -k "inflater or fixtures" 2>&1 | tail -8 | tee gpurun_out/${tag}_sanitizer_tiles.txt
 echo "== optimizer tests"; timeout 600 python -m pytest tests/test_optim.py -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/${tag}_pytest_optim.txt
 echo "== pytest gpu (all)"; timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/${tag}_pytest.txt
-echo "== tiles bench"; timeout 900 python benchmarks/tiles_bench.py 2>&1 | grep "^{" | tee gpurun_out/${tag}_tiles_bench.json | cut -c1-600
+echo "== tiles bench"; timeout 900 python bench.py --workload tiles 2>&1 | grep "^{" | tee gpurun_out/${tag}_tiles_bench.json | cut -c1-600
 echo "== ncu tiles"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lz4_frames|tile_assemble' -c 4 -f \
   -o gpurun_out/${tag}_tiles_prof python benchmarks/tiles_bench.py --steps 1 > gpurun_out/${tag}_ncu_tiles.log 2>&1

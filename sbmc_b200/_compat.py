@@ -1,7 +1,10 @@
-"""The two helpers the hot path takes from the external `ttools` package
-(torch-tools==0.0.36, not part of the reference tree and not installed here):
-`ttools.get_logger` (sbmc/modules.py:31, sbmc/functions.py:22) and
-`ttools.modules.image_operators.crop_like` (sbmc/models.py:27,206).
+"""What the reference takes from the external `ttools` package
+(torch-tools==0.0.36, not part of the reference tree and not installed here).
+The hot path uses two helpers: `ttools.get_logger` (sbmc/modules.py:31,
+sbmc/functions.py:22) and `ttools.modules.image_operators.crop_like`
+(sbmc/models.py:27,206).  The two scripts additionally use its checkpointer,
+trainer and callbacks (scripts/train.py:96-121, scripts/denoise.py:107,134-135):
+small equivalents are at the end of this file.
 """
 import logging
 

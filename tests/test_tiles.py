@@ -300,6 +300,63 @@ def test_oracle_reader_matches_reference_fixtures(name):
             check_item(exp, "%s/%d" % (name, i), item, i_diffuse_of(kw))
 
 
+# ------------------------------------------------------------------ GPU: the inflater through the C ABI
+def _gpu_inflate(frames, sizes):
+    table, total = layout(frames, sizes)
+    dev = th.device("cuda")
+    src = th.from_numpy(np.frombuffer(b"".join(frames) + b"\0", np.uint8).copy()).to(dev)
+    t = th.from_numpy(table).to(dev)
+    dst = th.zeros(total, dtype=th.uint8, device=dev)
+    status = th.full((len(frames),), -7, dtype=th.int32, device=dev)
+    before = _lib.launch_count()
+    _lib.check(_lib.load().sbmc_lz4_frames_inflate(
+        src.data_ptr(), t.data_ptr(), len(frames), dst.data_ptr(), status.data_ptr(),
+        th.cuda.current_stream().cuda_stream), "inflate")
+    th.cuda.synchronize()
+    assert _lib.launch_count() == before + 1
+    host = dst.cpu().numpy()
+    return [host[r[2]:r[2] + r[3]].tobytes() for r in table], status.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", FRAME_OPTIONS, ids=lambda o: "-".join(o) or "default")
+def test_gpu_inflater_matches_oracle(opts):
+    rng = np.random.default_rng(7)
+    raws = frame_corpus(rng)
+    if tile_io.liblz4() is not None:
+        frames = [tile_io.compress_frame(r, **opts) for r in raws]
+    else:
+        pa = pytest.importorskip("pyarrow")
+        frames = [pa.Codec("lz4").compress(r, asbytes=True) for r in raws]
+    for f, r in zip(frames, raws):
+        assert oracle.lz4_frame_decompress(f) == r
+    outs, status = _gpu_inflate(frames, [len(r) for r in raws])
+    assert not status.any(), status
+    assert outs == raws
+
+
+@pytest.mark.gpu
+def test_gpu_inflater_error_statuses_match_the_emulation():
+    raw = (b"sample-based monte carlo denoising " * 400)
+    frame = tile_io.compress_frame(raw) if tile_io.liblz4() else tile_io.stored_frame(raw)
+    n = len(raw)
+    hdr = bytearray(tile_io.stored_frame(raw))
+    hdr[6] ^= 0xFF                                   # header checksum byte
+    cases = [(frame[:len(frame) // 2], n), (b"\0\0\0\0junk", 10), (frame, n - 1), (frame, n + 1),
+             (frame + frame, 2 * n), (frame, n), (bytes(hdr), n)]
+    expect = [3, 1, 4, 6, 0, 0, 8]
+    if tile_io.liblz4() is not None:
+        good = tile_io.compress_frame(raw, content_checksum=True, block_checksum=True)
+        bad = bytearray(good)
+        bad[-1] ^= 0x01                              # content checksum
+        cases += [(good, n), (bytes(bad), n)]
+        expect += [0, 8]
+    _, want = emul_inflate([c[0] for c in cases], [c[1] for c in cases])
+    outs, got = _gpu_inflate([c[0] for c in cases], [c[1] for c in cases])
+    assert list(got) == list(want) == expect
+    assert outs[4] == raw + raw and outs[5] == raw
+
+
 # ------------------------------------------------------------------ the dataset classes, two backends
 class EmulBackend(object):
     """Stands in for sbmc_b200.datasets._CudaBackend: the two launches of an item
@@ -629,63 +686,7 @@ def test_tile_assemble_argument_validation_needs_no_gpu():
     assert lib.sbmc_lz4_frames_inflate(None, None, 2, None, None, None) == -1
 
 
-# ------------------------------------------------------------------ GPU: the product path
-def _gpu_inflate(frames, sizes):
-    table, total = layout(frames, sizes)
-    dev = th.device("cuda")
-    src = th.from_numpy(np.frombuffer(b"".join(frames) + b"\0", np.uint8).copy()).to(dev)
-    t = th.from_numpy(table).to(dev)
-    dst = th.zeros(total, dtype=th.uint8, device=dev)
-    status = th.full((len(frames),), -7, dtype=th.int32, device=dev)
-    before = _lib.launch_count()
-    _lib.check(_lib.load().sbmc_lz4_frames_inflate(
-        src.data_ptr(), t.data_ptr(), len(frames), dst.data_ptr(), status.data_ptr(),
-        th.cuda.current_stream().cuda_stream), "inflate")
-    th.cuda.synchronize()
-    assert _lib.launch_count() == before + 1
-    host = dst.cpu().numpy()
-    return [host[r[2]:r[2] + r[3]].tobytes() for r in table], status.cpu().numpy()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("opts", FRAME_OPTIONS, ids=lambda o: "-".join(o) or "default")
-def test_gpu_inflater_matches_oracle(opts):
-    rng = np.random.default_rng(7)
-    raws = frame_corpus(rng)
-    if tile_io.liblz4() is not None:
-        frames = [tile_io.compress_frame(r, **opts) for r in raws]
-    else:
-        pa = pytest.importorskip("pyarrow")
-        frames = [pa.Codec("lz4").compress(r, asbytes=True) for r in raws]
-    for f, r in zip(frames, raws):
-        assert oracle.lz4_frame_decompress(f) == r
-    outs, status = _gpu_inflate(frames, [len(r) for r in raws])
-    assert not status.any(), status
-    assert outs == raws
-
-
-@pytest.mark.gpu
-def test_gpu_inflater_error_statuses_match_the_emulation():
-    raw = (b"sample-based monte carlo denoising " * 400)
-    frame = tile_io.compress_frame(raw) if tile_io.liblz4() else tile_io.stored_frame(raw)
-    n = len(raw)
-    hdr = bytearray(tile_io.stored_frame(raw))
-    hdr[6] ^= 0xFF                                   # header checksum byte
-    cases = [(frame[:len(frame) // 2], n), (b"\0\0\0\0junk", 10), (frame, n - 1), (frame, n + 1),
-             (frame + frame, 2 * n), (frame, n), (bytes(hdr), n)]
-    expect = [3, 1, 4, 6, 0, 0, 8]
-    if tile_io.liblz4() is not None:
-        good = tile_io.compress_frame(raw, content_checksum=True, block_checksum=True)
-        bad = bytearray(good)
-        bad[-1] ^= 0x01                              # content checksum
-        cases += [(good, n), (bytes(bad), n)]
-        expect += [0, 8]
-    _, want = emul_inflate([c[0] for c in cases], [c[1] for c in cases])
-    outs, got = _gpu_inflate([c[0] for c in cases], [c[1] for c in cases])
-    assert list(got) == list(want) == expect
-    assert outs[4] == raw + raw and outs[5] == raw
-
-
+# ------------------------------------------------------------------ GPU: reader -> model
 @pytest.mark.gpu
 def test_gpu_dataset_feeds_the_denoiser():
     """FullImagesDataset -> DataLoader -> Multisteps, the denoise.py call chain

@@ -21,6 +21,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags():
+    """SBMC_B200_NVCC_FLAGS="-DSBMC_LZ4_WIDE_COPY ..." adds defines for A/B runs of
+    experimental paths (none is part of the default build)."""
+    return os.environ.get("SBMC_B200_NVCC_FLAGS", "").split()
+
+
 def _nvcc():
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -52,7 +58,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in _sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + _extra_flags() + ["-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(
             cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

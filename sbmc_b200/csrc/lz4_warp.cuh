@@ -107,7 +107,7 @@ SBMC_LZ4_FN uint32_t xxh32(const uint8_t *p, int64_t len) {
 
 // Copies n bytes src -> dst, lanes interleaved byte-wise (32 consecutive bytes
 // per warp access = one sector), four accesses in flight per lane.
-SBMC_LZ4_FN void copy_lanes(uint8_t *dst, const uint8_t *src, int64_t n) {
+SBMC_LZ4_FN void copy_bytes(uint8_t *dst, const uint8_t *src, int64_t n) {
   SBMC_LZ4_LANES(lane) {
     int64_t i = lane;
     for (; i + 96 < n; i += 128) {
@@ -120,6 +120,65 @@ SBMC_LZ4_FN void copy_lanes(uint8_t *dst, const uint8_t *src, int64_t n) {
     for (; i < n; i += 32) dst[i] = src[i];
   }
 }
+
+#if defined(SBMC_LZ4_WIDE_COPY)
+// Experimental (build with -DSBMC_LZ4_WIDE_COPY, off by default): long runs move
+// as 16-byte stores.  The destination is brought to 16-byte alignment byte-wise;
+// the source keeps an arbitrary alignment, so each 16-byte chunk is assembled
+// from five 4-byte-aligned words with a funnel shift.  The word window of a
+// chunk starts at most 3 bytes before its first source byte and ends at or
+// before src + n (the last chunks go byte-wise), so nothing outside
+// [src - 3, src + n) is read -- for a match (src = dst - offset, offset >= n)
+// that stays below dst.
+SBMC_LZ4_FN uint32_t load_aligned_u32(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t *>(p);
+#else
+  uint32_t v;
+  __builtin_memcpy(&v, p, 4);
+  return v;
+#endif
+}
+
+SBMC_LZ4_FN uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, shift);
+#else
+  return shift ? (uint32_t)((((uint64_t)hi << 32) | lo) >> shift) : lo;
+#endif
+}
+
+SBMC_LZ4_FN void copy_lanes(uint8_t *dst, const uint8_t *src, int64_t n) {
+  if (n < 256) {
+    copy_bytes(dst, src, n);
+    return;
+  }
+  const int64_t head = (int64_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+  const int64_t chunks = (n - head - 3) / 16;     // chunks whose word window ends inside src
+  copy_bytes(dst, src, head);
+  SBMC_LZ4_LANES(lane) {
+    for (int64_t c = lane; c < chunks; c += 32) {
+      const uint8_t *s = src + head + 16 * c;
+      const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+      const uint8_t *a = s - (shift >> 3);
+      const uint32_t w0 = load_aligned_u32(a), w1 = load_aligned_u32(a + 4),
+                     w2 = load_aligned_u32(a + 8), w3 = load_aligned_u32(a + 12);
+      const uint32_t w4 = shift ? load_aligned_u32(a + 16) : 0u;
+      uint32_t out[4] = {funnel_r(w0, w1, shift), funnel_r(w1, w2, shift),
+                         funnel_r(w2, w3, shift), funnel_r(w3, w4, shift)};
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<uint4 *>(dst + head + 16 * c) = make_uint4(out[0], out[1], out[2], out[3]);
+#else
+      __builtin_memcpy(dst + head + 16 * c, out, 16);
+#endif
+    }
+  }
+  const int64_t done = head + 16 * chunks;
+  copy_bytes(dst + done, src + done, n - done);
+}
+#else
+SBMC_LZ4_FN void copy_lanes(uint8_t *dst, const uint8_t *src, int64_t n) { copy_bytes(dst, src, n); }
+#endif
 
 // dst[0..n) = the `offset` bytes before dst, repeated.  Reads stay below dst.
 SBMC_LZ4_FN void match_lanes(uint8_t *dst, int64_t offset, int64_t n) {

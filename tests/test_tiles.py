@@ -44,18 +44,21 @@ needs_liblz4 = pytest.mark.skipif(tile_io.liblz4() is None, reason="system liblz
 
 
 # ------------------------------------------------------------------ helpers
-def emul(reverse_lanes=False):
+def emul(reverse_lanes=False, wide=False):
     """tests/native/tiles_emul.cpp built with g++ (device sources on the host);
-    `reverse_lanes` runs the 32 lanes of the inflater from 31 down to 0."""
+    `reverse_lanes` runs the 32 lanes of the inflater from 31 down to 0, `wide`
+    builds the experimental 16-byte copy path (-DSBMC_LZ4_WIDE_COPY)."""
     src = os.path.join(HERE, "native", "tiles_emul.cpp")
-    out = os.path.join(HERE, "native", "libtiles_emul%s.so" % ("_rev" if reverse_lanes else ""))
+    out = os.path.join(HERE, "native", "libtiles_emul%s%s.so" % (
+        "_rev" if reverse_lanes else "", "_wide" if wide else ""))
     deps = [src] + [os.path.join(HERE, "..", "sbmc_b200", "csrc", f)
                     for f in ("lz4_warp.cuh", "tiles_body.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = "/usr/local/cuda/include"
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-I", cuda_inc, "-o", out, src]
-                              + (["-DSBMC_LZ4_REVERSE_LANES"] if reverse_lanes else []))
+                              + (["-DSBMC_LZ4_REVERSE_LANES"] if reverse_lanes else [])
+                              + (["-DSBMC_LZ4_WIDE_COPY"] if wide else []))
     lib = ctypes.CDLL(out)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.emul_lz4_frames_inflate.argtypes = [vp, vp, i64, vp, vp]
@@ -96,13 +99,13 @@ def layout(frames, sizes):
     return np.array(table, np.int64).reshape(-1, 4), max(do, 16)
 
 
-def emul_inflate(frames, sizes, reverse_lanes=False):
+def emul_inflate(frames, sizes, reverse_lanes=False, wide=False):
     table, total = layout(frames, sizes)
     src = np.frombuffer(b"".join(frames) + b"\0", np.uint8)
     dst = np.zeros(total, np.uint8)
     status = np.zeros(len(frames), np.int32)
     vp = ctypes.c_void_p
-    emul(reverse_lanes).emul_lz4_frames_inflate(
+    emul(reverse_lanes, wide).emul_lz4_frames_inflate(
         src.ctypes.data_as(vp), table.ctypes.data_as(vp), len(frames), dst.ctypes.data_as(vp),
         status.ctypes.data_as(vp))
     return [dst[t[2]:t[2] + t[3]].tobytes() for t in table], status
@@ -201,6 +204,10 @@ def test_lz4_oracle_and_emulated_warp_inflater_match_liblz4(opts):
     # (on the GPU they run concurrently): same bytes with the lanes reversed
     outs, status = emul_inflate(frames, [len(r) for r in raws], reverse_lanes=True)
     assert not status.any() and outs == raws
+    # the experimental 16-byte copy path (off in the product build) gives the same bytes
+    for rev in (False, True):
+        outs, status = emul_inflate(frames, [len(r) for r in raws], reverse_lanes=rev, wide=True)
+        assert not status.any() and outs == raws
 
 
 def test_lz4_default_preferences_are_the_reference_writers():

@@ -19,3 +19,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lz4
 tail -2 gpurun_out/${tag}_ncu_tiles.log
 echo "== bench"; timeout 900 python bench.py 2> gpurun_out/${tag}_bench.err | grep "^{" | tee gpurun_out/${tag}_bench.json | cut -c1-300
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 2 | tee gpurun_out/${tag}_bench_ref.json | cut -c1-200
+echo "== A/B: experimental 16-byte copies in the inflater (not the default build)"
+SBMC_B200_NVCC_FLAGS="-DSBMC_LZ4_WIDE_COPY" python -c "from sbmc_b200 import build; build.build(force=True)" > /dev/null 2>&1
+timeout 600 python -m pytest tests/test_tiles.py -m gpu -q -x -k "inflater or fixtures" 2>&1 | tail -3 | tee gpurun_out/${tag}_pytest_tiles_wide.txt
+timeout 900 python benchmarks/tiles_bench.py 2>&1 | grep "^{" | tee gpurun_out/${tag}_tiles_bench_wide.json | cut -c1-600
+python -c "from sbmc_b200 import build; build.build(force=True)" > /dev/null 2>&1   # back to the default build

@@ -36,7 +36,11 @@ struct TileAssembleParams {
   int preprocess;           // 1: log-compress the radiance channels (sbmc mode)
   int aligned16;            // every base pointer / offset allows 16-byte accesses
   float *features, *radiance, *low_spp, *image_data, *image_data_var, *target_image;
-  short chan_src[SBMC_TILE_MAX_FEATURES];
+  short chan_src[SBMC_TILE_MAX_FEATURES];   // per output channel: source plane / BT_BASE + k
+  // the same selection regrouped for the kernel's two loops
+  short fl_out[SBMC_TILE_MAX_FEATURES], fl_src[SBMC_TILE_MAX_FEATURES];  // plain fp32 planes
+  int n_fl;                 // ... how many (radiance excluded: it has its own code)
+  int i_bt;                 // output channel of the first bounce-type plane, -1: none
 };
 
 // Fills *p.  Returns 0 = launch, 1 = nothing to do, negative = SBMC_E*.
@@ -104,6 +108,18 @@ static inline int tile_assemble_params(TileAssembleParams *p, const void *raw,
     set_error("tile assembly: sample stride %lld smaller than a sample frame (%lld)",
               (long long)sample_stride_bytes, need);
     return SBMC_EINVAL;
+  }
+  p->n_fl = 0;
+  p->i_bt = -1;
+  for (int f = 0; f < nf; ++f) {
+    if (f >= p->i_diffuse && f < p->i_diffuse + 6) continue;
+    if (cs[f] >= SBMC_TILE_BT_BASE) {
+      if (p->i_bt < 0) p->i_bt = f;
+      continue;
+    }
+    p->fl_out[p->n_fl] = (short)f;
+    p->fl_src[p->n_fl] = cs[f];
+    ++p->n_fl;
   }
   p->raw = static_cast<const uint8_t *>(raw);
   p->tiles = reinterpret_cast<const long long *>(tile_table);
@@ -245,27 +261,46 @@ SBMC_HD void tile_assemble_body(const TileAssembleParams &p, long long tile, int
       px_store<VEC>(fout + (long long)(p.i_diffuse + c) * plane_out, od);
       px_store<VEC>(fout + (long long)(p.i_diffuse + 3 + c) * plane_out, os);
     }
-    for (int f = 0; f < p.nf; ++f) {
-      if (f >= p.i_diffuse && f < p.i_diffuse + 6) continue;  // written above
-      const int src = p.chan_src[f];
-      Px<VEC> o;
-      if (src < SBMC_TILE_BT_BASE) {
-        o = px_load<VEC>(fl + (long long)src * plane_in + in_px);
-      } else {
-        const int k = src - SBMC_TILE_BT_BASE;
-        const int flag = k / p.depth, vertex = k - flag * p.depth;
+    // Plain planes (coordinates, g-buffer, probabilities, light directions):
+    // four loads in flight, then four stores.
+    for (int k0 = 0; k0 < p.n_fl; k0 += 4) {
+      Px<VEC> v[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < p.n_fl)
+          v[j] = px_load<VEC>(fl + (long long)p.fl_src[k0 + j] * plane_in + in_px);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < p.n_fl) px_store<VEC>(fout + (long long)p.fl_out[k0 + j] * plane_out, v[j]);
+    }
+    // Bounce types: one int16 plane per path vertex -> five 0 / 1 planes
+    // (reflection, transmission, diffuse, glossy, specular), flag-major.
+    if (p.i_bt >= 0) {
+      for (int vertex = 0; vertex < p.depth; ++vertex) {
         const short *q = bt + (long long)vertex * plane_in + in_px;
+        int bits[VEC];
         if (VEC == 4) {
           const short4 t = *reinterpret_cast<const short4 *>(q);
-          o.v[0] = (float)((t.x >> flag) & 1);
-          o.v[1 % VEC] = (float)((t.y >> flag) & 1);
-          o.v[2 % VEC] = (float)((t.z >> flag) & 1);
-          o.v[3 % VEC] = (float)((t.w >> flag) & 1);
+          bits[0] = t.x;
+          bits[1 % VEC] = t.y;
+          bits[2 % VEC] = t.z;
+          bits[3 % VEC] = t.w;
         } else {
-          for (int i = 0; i < VEC; ++i) o.v[i] = (float)((q[i] >> flag) & 1);
+          for (int i = 0; i < VEC; ++i) bits[i] = q[i];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int flag = 0; flag < 5; ++flag) {
+          Px<VEC> o;
+          for (int i = 0; i < VEC; ++i) o.v[i] = (float)((bits[i] >> flag) & 1);
+          px_store<VEC>(fout + (long long)(p.i_bt + flag * p.depth + vertex) * plane_out, o);
         }
       }
-      px_store<VEC>(fout + (long long)f * plane_out, o);
     }
   }
   const float count = (float)p.spp;

@@ -24,6 +24,7 @@ There is no CPU data path: reading an item without the CUDA library raises.
 """
 import os
 import struct
+import threading
 
 import numpy as np
 import torch as th
@@ -34,7 +35,7 @@ from ._compat import get_logger
 
 LOG = get_logger(__name__)
 
-__all__ = ["TilesDataset", "FullImagesDataset", "MultiSampleCountDataset"]
+__all__ = ["TilesDataset", "FullImagesDataset", "MultiSampleCountDataset", "PrefetchLoader"]
 
 _HEADER = struct.Struct("<9i4f")       # metadata (9 x int32) + global features (4 x float32)
 _META_FIELDS = ("version", "tile_size", "image_width", "image_height", "sample_count",
@@ -65,20 +66,22 @@ class _Staging(object):
         return self.buf
 
 
-_STAGING = _Staging()
+_STAGING = _Staging()      # items read directly (dataset[i], DataLoader) stage here
 
 # Threads that read tile files into the staging buffer (the only host work of an
 # item that scales with its size; `readinto` releases the GIL).
 _IO_THREADS = max(1, min(16, (os.cpu_count() or 1)))
 _POOL = None
+_POOL_LOCK = threading.Lock()
 
 
 def _io_pool():
     global _POOL
-    if _POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=_IO_THREADS, thread_name_prefix="sbmc-tiles")
-    return _POOL
+    with _POOL_LOCK:        # the main thread and a loader's planner thread both get here
+        if _POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _POOL = ThreadPoolExecutor(max_workers=_IO_THREADS, thread_name_prefix="sbmc-tiles")
+        return _POOL
 
 
 class _CudaBackend(object):
@@ -329,11 +332,13 @@ class TilesDataset(Dataset):
                 pos += 4 + nbytes
         return min(pos, size)
 
-    def _plan(self, fnames):
-        """Reads the files (only the chunks of the first `spp` samples) into the
+    def _plan(self, fnames, staging=None):
+        """Reads the files (only the chunks of the first `spp` samples) into a
         pinned staging buffer -- in parallel, file reads release the GIL -- and
-        walks their chunk headers.  Returns (staging view, frame table rows,
-        per-tile records, inflated bytes)."""
+        walks their chunk headers.  Pure host work (no CUDA call): PrefetchLoader
+        runs it on a background thread, into its own buffers, while the GPU is busy
+        with the previous item.
+        Returns (staging view, frame table rows, per-tile records, inflated bytes)."""
         workers = min(_IO_THREADS, len(fnames))
         pool = _io_pool() if workers > 1 else None
         needed = list(pool.map(self._needed_bytes, fnames)) if pool else \
@@ -342,7 +347,7 @@ class TilesDataset(Dataset):
         for need in needed:
             offsets.append(total)
             total += _align(need, 16)
-        stage = _STAGING.get(total)
+        stage = (staging or _STAGING).get(total)
         host = stage.numpy()
 
         def read(job):
@@ -393,15 +398,16 @@ class TilesDataset(Dataset):
             tiles.append(record)
         return stage[:max(total, 1)], frames, tiles, dst
 
-    def _read_tiles(self, fnames, height, width, positions=None, row0=0, clip_rows=False):
+    def _read_tiles(self, fnames, height, width, positions=None, row0=0, clip_rows=False,
+                    planned=None):
         """Inflates and assembles `fnames` into one set of [.., height, width]
         tensors holding image rows row0 .. row0 + height - 1; `positions` overrides
         the tiles' (block_x, block_y).  With `clip_rows` tiles may stick out of the
         row range (their rows outside are skipped: a rank's band), otherwise every
-        tile must fit."""
+        tile must fit.  `planned` is the result of an earlier `_plan(fnames)`."""
         backend = _backend(self.device)
         dev = backend.device
-        stage, frames, tiles, raw_bytes = self._plan(fnames)
+        stage, frames, tiles, raw_bytes = planned if planned is not None else self._plan(fnames)
         ts, spp = self.tile_size, self.spp
         nchans = self.pixel_features // 2
         nf = len(self.labels)
@@ -455,11 +461,11 @@ class TilesDataset(Dataset):
         return th.tensor([gfeatures[k] for k in self.glabels], dtype=th.float32,
                          device=dev).reshape(len(self.glabels), 1, 1)
 
-    def _get_raw_data(self, idx):
+    def _get_raw_data(self, idx, planned=None):
         """One tile as the reference's raw sample dict (datasets.py:401-456)."""
         fname = self._filename(idx)
         ts = self.tile_size
-        out, tiles = self._read_tiles([fname], ts, ts, positions=[(0, 0)])
+        out, tiles = self._read_tiles([fname], ts, ts, positions=[(0, 0)], planned=planned)
         t = tiles[0]
         dev = out["target_image"].device
         sample = {"block_x": t["block_x"], "block_y": t["block_y"],
@@ -476,16 +482,18 @@ class TilesDataset(Dataset):
             sample = self._preprocess_kpcn(sample)
         return sample       # the sbmc-mode log compression ran inside the assembly kernel
 
-    def __getitems__(self, indices):
+    def __getitems__(self, indices, planned=None):
         """Batched fetch (the DataLoader calls this once per batch when it exists):
         all tiles of the batch are inflated and assembled by one pair of launches,
         stacked along rows of one scratch image; every sample is its slice."""
         indices = list(indices)
-        if self.mode == TilesDataset.KPCN_MODE or len(indices) <= 1:
+        if self.mode == TilesDataset.KPCN_MODE:
             return [self[i] for i in indices]
+        if len(indices) == 1:
+            return [self._get_raw_data(indices[0], planned=planned)]
         ts = self.tile_size
         fnames = [self._filename(i) for i in indices]
-        out, tiles = self._read_tiles(fnames, ts * len(fnames), ts,
+        out, tiles = self._read_tiles(fnames, ts * len(fnames), ts, planned=planned,
                                       positions=[(0, i * ts) for i in range(len(fnames))])
         dev = out["target_image"].device
         samples = []
@@ -591,15 +599,19 @@ class FullImagesDataset(Dataset):
     def get_scene_name(self, idx):
         return self.scenes[idx]
 
-    def __getitem__(self, idx):
+    def _scene_files(self, idx):
+        d = self.tiles_dset
+        start, end = d.indices[self.scenes[idx]]
+        return [d._filename(i) for i in range(start, end)]
+
+    def __getitem__(self, idx, planned=None):
         d = self.tiles_dset
         scene = self.scenes[idx]
         start, end = d.indices[scene]
         height, width, ts = d.image_height, d.image_width, d.tile_size
         if d.mode == TilesDataset.KPCN_MODE:
             return self._paste_tiles(start, end)
-        fnames = [d._filename(i) for i in range(start, end)]
-        out, tiles = d._read_tiles(fnames, height, width)
+        out, tiles = d._read_tiles(self._scene_files(idx), height, width, planned=planned)
         dev = out["target_image"].device
         first = tiles[0]["gfeatures"]
         sample = {"global_features": d._global_features(first, dev),
@@ -715,3 +727,81 @@ class MultiSampleCountDataset(ConcatDataset):
         self.labels, self.glabels, self.version = first.labels, first.glabels, first.version
         self.num_features = first.num_features
         self.num_global_features = first.num_global_features
+
+
+class PrefetchLoader(object):
+    """Iterates a dataset of this module in batches like
+    `DataLoader(dataset, batch_size, shuffle, num_workers=0)` (same collation),
+    with the host half of batch i+1 -- reading its tile files into the second
+    staging buffer and walking their chunk tables -- running on a background
+    thread while batch i is inflated, assembled and consumed on the GPU.  (An
+    extra on top of the reference's interface: its DataLoader workers overlapped
+    the CPU decoding the same way; here only file reads are left on the host.)
+
+    TilesDataset: any batch size.  FullImagesDataset and MultiSampleCountDataset:
+    batch_size = 1 (the sample dimension varies / images are whole).  kpcn mode has
+    no split host half and is iterated plainly."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, drop_last=False, generator=None):
+        if batch_size < 1:
+            raise ValueError("batch_size must be positive")
+        if not isinstance(dataset, TilesDataset) and batch_size != 1:
+            raise ValueError("batch_size must be 1 for %s" % type(dataset).__name__)
+        self.dataset, self.batch_size = dataset, batch_size
+        self.shuffle, self.drop_last, self.generator = shuffle, drop_last, generator
+        # while the copy / kernels of one batch read the first buffer, the files of
+        # the next batch are read into the second; both belong to this loader only
+        self._stagings = (_Staging(), _Staging())
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _resolve(self, idx):
+        """-> (tiles dataset or full-images dataset, local index)."""
+        d = self.dataset
+        if isinstance(d, ConcatDataset):
+            import bisect
+            which = bisect.bisect_right(d.cumulative_sizes, idx)
+            return d.datasets[which], idx - (d.cumulative_sizes[which - 1] if which else 0)
+        return d, idx
+
+    def _host_half(self, batch, slot, cuda_device=None):
+        if cuda_device is not None:     # pinned allocations belong to the caller's device
+            th.cuda.set_device(cuda_device)
+        d, first = self._resolve(batch[0])
+        tiles = d.tiles_dset if isinstance(d, FullImagesDataset) else d
+        if tiles.mode == TilesDataset.KPCN_MODE:
+            return None
+        if isinstance(d, FullImagesDataset):
+            return tiles._plan(d._scene_files(first), self._stagings[slot])
+        return tiles._plan([d._filename(self._resolve(i)[1]) for i in batch], self._stagings[slot])
+
+    def _device_half(self, batch, planned):
+        d, first = self._resolve(batch[0])
+        if isinstance(d, FullImagesDataset):
+            return [d.__getitem__(first, planned=planned)]
+        if planned is None:
+            return [d[self._resolve(i)[1]] for i in batch]
+        return d.__getitems__([self._resolve(i)[1] for i in batch], planned=planned)
+
+    def __iter__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        from torch.utils.data import default_collate
+        n = len(self.dataset)
+        order = th.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
+        batches = [order[i:i + self.batch_size] for i in range(0, n, self.batch_size)]
+        if self.drop_last and batches and len(batches[-1]) < self.batch_size:
+            batches.pop()
+        if not batches:
+            return
+        # one planner thread, distinct from the file-read pool it fans out to
+        cuda_device = th.cuda.current_device() if th.cuda.is_available() else None
+        with ThreadPoolExecutor(max_workers=1, thread_name_prefix="sbmc-plan") as planner:
+            pending = planner.submit(self._host_half, batches[0], 0, cuda_device)
+            for i, batch in enumerate(batches):
+                planned = pending.result()
+                if i + 1 < len(batches):
+                    pending = planner.submit(self._host_half, batches[i + 1], (i + 1) % 2,
+                                             cuda_device)
+                yield default_collate(self._device_half(batch, planned))

@@ -59,7 +59,8 @@ def main(args):
                                   splat=not args.gather, pixel=args.pixel)
         model_params = dict(ksize=args.ksize, gather=args.gather, pixel=args.pixel)
 
-    loader = DataLoader(data, batch_size=args.bs, num_workers=0, shuffle=True)
+    # the next batch's tile files are read while the current step runs on the GPU
+    loader = datasets.PrefetchLoader(data, batch_size=args.bs, shuffle=True)
     val_loader = None
     if args.val_data is not None:
         val = datasets.TilesDataset(args.val_data, **data_args)

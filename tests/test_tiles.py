@@ -521,6 +521,52 @@ def test_batched_fetch_equals_single_items(backend):
                 assert batch[k][i].item() == pytest.approx(v)
 
 
+def _same_batch(a, b):
+    assert set(a) == set(b)
+    for k, v in a.items():
+        if isinstance(v, th.Tensor):
+            assert th.equal(v, b[k]), k
+        else:
+            assert v == b[k], k
+
+
+def test_prefetch_loader_equals_the_dataloader(backend):
+    """PrefetchLoader overlaps the next batch's file reads with the current batch:
+    same batches, same order, same collation as DataLoader(num_workers=0)."""
+    from torch.utils.data import DataLoader
+    tiles = datasets.TilesDataset(DATA, spp=2)
+    got = list(datasets.PrefetchLoader(tiles, batch_size=3))
+    want = list(DataLoader(tiles, batch_size=3, shuffle=False, num_workers=0))
+    assert len(got) == len(want) == len(datasets.PrefetchLoader(tiles, batch_size=3)) == 3
+    for a, b in zip(got, want):
+        _same_batch(a, b)
+    assert len(list(datasets.PrefetchLoader(tiles, batch_size=3, drop_last=True))) == 2
+    g = th.Generator().manual_seed(3)
+    order = th.randperm(len(tiles), generator=th.Generator().manual_seed(3)).tolist()
+    shuffled = list(datasets.PrefetchLoader(tiles, batch_size=1, shuffle=True, generator=g))
+    assert [b["path"][0] for b in shuffled] == [tiles._filename(i) for i in order]
+    full = datasets.FullImagesDataset(DATA)
+    for a, b in zip(datasets.PrefetchLoader(full), DataLoader(full, batch_size=1, num_workers=0)):
+        _same_batch(a, b)
+    multi = datasets.MultiSampleCountDataset(DATA, spp=3)
+    spps = [int(b["spp"].reshape(-1)[0]) for b in datasets.PrefetchLoader(multi)]
+    assert spps == expected()["multi/spp_of_items"].tolist()
+    kp = datasets.TilesDataset(DATA, mode="kpcn", spp=2)
+    a = next(iter(datasets.PrefetchLoader(kp, batch_size=2)))
+    b = next(iter(DataLoader(kp, batch_size=2, num_workers=0)))
+    _same_batch(a, b)
+    with pytest.raises(ValueError):
+        datasets.PrefetchLoader(full, batch_size=2)
+    # direct reads interleaved with a live prefetching iteration (e.g. validation
+    # inside a training epoch) do not share its staging buffers
+    it = iter(datasets.PrefetchLoader(tiles, batch_size=3))
+    first = next(it)
+    probe = tiles[7]                   # main-thread read while batch 2 is being planned
+    _same_batch(first, want[0])
+    _same_batch(next(it), want[1])
+    assert th.equal(probe["features"], want[2]["features"][1])
+
+
 def test_corrupt_tile_raises_like_the_reference(tmp_path, backend):
     src = fixture_files(False)[0]
     folder = tmp_path / "scene"

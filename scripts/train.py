@@ -95,6 +95,14 @@ def parser():
     p.add_argument("--bs", type=int, default=1)
     p.add_argument("--num_epochs", type=int)
     p.add_argument("--max_steps", type=int, help="stop after this many steps (extra).")
+    # accepted so that the reference's command lines keep working; without effect here:
+    # samples are decoded on the GPU (no loader workers), training is CUDA-only, no Visdom
+    p.add_argument("--num_worker_threads", type=int, default=0, help=argparse.SUPPRESS)
+    p.add_argument("--cuda", action="store_true", default=True, help=argparse.SUPPRESS)
+    p.add_argument("--env", default=None, help=argparse.SUPPRESS)
+    p.add_argument("--port", type=int, default=None, help=argparse.SUPPRESS)
+    p.add_argument("--debug", action="store_true", default=False,
+                   help="verbose logging (ttools.set_logger(debug)).")
     p.add_argument("--log_every", type=int, default=50)
     p.add_argument("--display_every", type=int, default=0,
                    help="write a low-spp / output / target / difference gallery every N steps.")
@@ -115,4 +123,8 @@ def parser():
 
 
 if __name__ == "__main__":
-    main(parser().parse_args())
+    _args = parser().parse_args()
+    if _args.debug:
+        import logging
+        logging.getLogger().setLevel(logging.DEBUG)
+    main(_args)

@@ -186,7 +186,8 @@ def test_script_parsers_keep_the_reference_options():
         ["--input", "i", "--checkpoint", "c", "--output", "o.exr", "--spp", "4"])
     assert (d.tile_size, d.tile_pad, d.spp) == (1024, 256, 4)
     t = load_script("train").parser().parse_args(
-        ["--data", "d", "--checkpoint_dir", "c", "--constant_spp", "--dont_use_bt", "--gather"])
+        ["--data", "d", "--checkpoint_dir", "c", "--constant_spp", "--dont_use_bt", "--gather",
+         "--num_worker_threads", "4", "--cuda", "--env", "sbmc", "--port", "8097", "--debug"])
     assert (t.spp, t.ksize, t.randomize_spp, t.load_bt, t.load_p, t.gather, t.lr) == (
         8, 21, False, False, True, True, 1e-4)
 

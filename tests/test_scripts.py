@@ -254,3 +254,37 @@ def test_train_then_denoise_scripts(tmp_path, backend, fused_optimizer, monkeypa
     # tiles see 8 pixels of context where the U-nets would want ~120: the two runs
     # agree only roughly -- what is checked is the stitching (no seams of zeros)
     assert np.count_nonzero(outs["tiled"][1:-1, 1:-1]) > 0.99 * 46 * 46 * 3
+
+
+def test_kpcn_mode_scripts(tmp_path, backend):
+    """The [Bako2017] comparison path of both scripts (train.py --kpcn_mode,
+    denoise.py reading kpcn_mode from the checkpoint's meta; Makefile:167-173,112-116
+    of the reference)."""
+    root = _scene(tmp_path, ts=48, nx=1, ny=1, spp=2)
+    train = load_script("train")
+    denoise = load_script("denoise")
+    if backend == "host-emulation":
+        import unittest.mock as mock
+        patches = [mock.patch.object(train, "_device", lambda: "cpu"),
+                   mock.patch.object(denoise, "_device", lambda: "cpu")]
+    else:
+        patches = []
+    for p_ in patches:
+        p_.start()
+    try:
+        ckpt = str(tmp_path / "ckpt")
+        train.main(train.parser().parse_args(
+            ["--data", root, "--checkpoint_dir", ckpt, "--constant_spp", "--spp", "2", "--bs", "1",
+             "--kpcn_mode", "--ksize", "3", "--num_epochs", "1", "--max_steps", "1"]))
+        meta = _compat.Checkpointer.load_meta(ckpt)
+        assert meta["kpcn_mode"] is True and meta["data_params"]["mode"] == "kpcn"
+        out = str(tmp_path / "kpcn.exr")
+        denoise.main(denoise.parser().parse_args(
+            ["--input", os.path.join(root, "scene"), "--checkpoint", ckpt, "--output", out]))
+        img = imageio.read_exr(out)
+        # nine unpadded 5x5 convolutions crop 18 pixels per side (the gather kernel none)
+        assert img.shape == (48, 48, 3) and np.isfinite(img).all()
+        assert not img[:18].any() and not img[:, :18].any() and img[18:-18, 18:-18].all()
+    finally:
+        for p_ in patches:
+            p_.stop()

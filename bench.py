@@ -144,70 +144,85 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # the reference arm / cpu_baseline: the CPU restatement on the host cores
 # --------------------------------------------------------------------------
-def cpu_sample(a, target_seconds, reps_min=1):
-    """Times oracle fwd+bwd on one image of the workload ([1,C,H,W] x
-    [1,K,K,H,W]); returns (Msamples/s, cores, description, seconds per rep)."""
-    import torch as th
-    import oracle
-    th.manual_seed(0)
-    data = 2 * th.randn(1, a.c, a.h, a.w)
-    weights = th.randn(1, a.k, a.k, a.h, a.w)
-    d_out = th.randn(1, a.c, a.h, a.w)
-    d_sw = th.randn(1, a.h, a.w)
-    out = th.empty_like(data); sum_w = th.empty(1, a.h, a.w)
-    d_data = th.empty_like(data); d_weights = th.empty_like(weights)
+def host_cores():
+    """The host cores this process may run on (the affinity mask, not what a
+    launcher wrote into OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
-    def once():
-        oracle.kernel_weighting_cpu_float32(data, weights, out, sum_w)
-        oracle.kernel_weighting_grad_cpu_float32(data, weights, sum_w, d_out, d_sw,
-                                                 d_data, d_weights)
-    once()                                   # warm-up (page faults, thread pool)
-    t0 = time.perf_counter(); once(); one = time.perf_counter() - t0
+
+class CpuArm:
+    """The ONE routine both CPU legs time (`cpu_baseline` of the B200 line and
+    `--impl reference`): the oracle's fwd+bwd on one image of the workload
+    ([1,C,H,W] x [1,K,K,H,W]) with every host core, whatever OMP_NUM_THREADS says."""
+
+    def __init__(self, a):
+        import torch as th
+        import oracle
+        self.a, self.oracle = a, oracle
+        oracle.set_num_threads(host_cores())
+        self.cores = oracle.num_threads()
+        th.manual_seed(0)
+        self.data = 2 * th.randn(1, a.c, a.h, a.w)
+        self.weights = th.randn(1, a.k, a.k, a.h, a.w)
+        self.d_out = th.randn(1, a.c, a.h, a.w)
+        self.d_sw = th.randn(1, a.h, a.w)
+        self.out = th.empty_like(self.data)
+        self.sum_w = th.empty(1, a.h, a.w)
+        self.d_data = th.empty_like(self.data)
+        self.d_weights = th.empty_like(self.weights)
+        self.once()                              # page faults, thread pool
+        self.once()
+
+    def once(self):
+        o = self.oracle
+        t0 = time.perf_counter()
+        o.kernel_weighting_cpu_float32(self.data, self.weights, self.out, self.sum_w)
+        o.kernel_weighting_grad_cpu_float32(self.data, self.weights, self.sum_w, self.d_out,
+                                            self.d_sw, self.d_data, self.d_weights)
+        return time.perf_counter() - t0
+
+    def run(self, reps):
+        """Median seconds per image over `reps` repetitions."""
+        ts = sorted(self.once() for _ in range(reps))
+        return ts[len(ts) // 2]
+
+    def describe(self, reps):
+        a = self.a
+        return ("each step = 1 image of the workload ([1,%d,%d,%d]x[1,%d,%d,%d,%d], fwd+bwd) "
+                "instead of B*spp=%d; median of %d; %d OpenMP threads; C restatement of the "
+                "Halide CPU schedule (oracle/sbmc_oracle.c)"
+                % (a.c, a.h, a.w, a.k, a.k, a.h, a.w, a.b * a.spp, reps, self.cores))
+
+
+def cpu_sample(a, target_seconds, reps_min=3):
+    """(Msamples/s, cores, description, seconds per image) of the CPU arm."""
+    arm = CpuArm(a)
+    one = arm.once()
     reps = max(reps_min, min(50, int(target_seconds / max(one, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        once()
-    dt = (time.perf_counter() - t0) / reps
-    samples = a.h * a.w
-    desc = ("1 of the %d images of one call: [1,%d,%d,%d]x[1,%d,%d,%d,%d] fwd+bwd, "
-            "%d reps, OpenMP C restatement of the Halide CPU schedule (oracle/sbmc_oracle.c)"
-            % (a.b, a.c, a.h, a.w, a.k, a.k, a.h, a.w, reps))
-    return samples / dt / 1e6, oracle.num_threads(), desc, dt
+    dt = arm.run(reps)
+    return a.h * a.w / dt / 1e6, arm.cores, arm.describe(reps), dt
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t_steps = []
-    import torch as th
-    import oracle
-    th.manual_seed(0)
-    data = 2 * th.randn(1, a.c, a.h, a.w)
-    weights = th.randn(1, a.k, a.k, a.h, a.w)
-    d_out = th.randn(1, a.c, a.h, a.w)
-    d_sw = th.randn(1, a.h, a.w)
-    out = th.empty_like(data); sum_w = th.empty(1, a.h, a.w)
-    d_data = th.empty_like(data); d_weights = th.empty_like(weights)
-    for i in range(a.warmup + a.steps):
-        t0 = time.perf_counter()
-        oracle.kernel_weighting_cpu_float32(data, weights, out, sum_w)
-        oracle.kernel_weighting_grad_cpu_float32(data, weights, sum_w, d_out, d_sw,
-                                                 d_data, d_weights)
-        if i >= a.warmup:
-            t_steps.append(time.perf_counter() - t0)
-    dt = sum(t_steps) / len(t_steps)
+    arm = CpuArm(a)
+    for _ in range(a.warmup):
+        arm.once()
+    dt = arm.run(a.steps)
     value = a.h * a.w / dt / 1e6
-    sample = ("each step = 1 image of the workload ([1,%d,%d,%d]x[1,%d,%d,%d,%d], fwd+bwd) "
-              "instead of B*spp=%d" % (a.c, a.h, a.w, a.k, a.k, a.h, a.w, a.b * a.spp))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload(a),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(),
-                         "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores,
+                         "kind": "port", "sample": arm.describe(a.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "note": "Halide (the reference's code generator) cannot be built here; this is "

@@ -74,9 +74,102 @@ def bench_chains(a, dev):
             "rel_err_vs_fp32": rel}), flush=True)
 
 
+def bench_chains_v3(a, dev):
+    """The pipelined all-samples chain kernel (csrc/chain_v3.cu) on one 720p image with
+    `spp` samples: time per sample plane against the kernel's own HBM roofline and
+    against the round-1 serial per-sample kernel on the same bf16 NHWC tensors."""
+    from sbmc_b200 import conv1x1, modules
+    h, w, spp = a.h or 720, a.w or 1280, a.spp or 4
+    hw = h * w
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(
+            os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, ValueError, KeyError):
+        peak = 6650.0
+    emb = modules.ConvChain(256, 128, width=128, depth=3, ksize=1, pad=False).to(dev).eval()
+    emb0 = modules.ConvChain(96, 128, width=128, depth=3, ksize=1, pad=False).to(dev).eval()
+    reg = modules.ConvChain(256, 441, depth=3, width=128, ksize=1, activation="leaky_relu",
+                            pad=False, output_type="linear").to(dev).eval()
+    feats = th.randn(1, spp, hw, 128, device=dev).to(th.bfloat16)
+    prop = th.randn(1, hw, 128, device=dev).to(th.bfloat16)
+    gf = th.randn(1, 3, device=dev)
+    out = th.empty_like(feats)
+    logits = th.empty(1, spp, 441, hw, device=dev)
+    one = th.empty(1, 441, hw, device=dev)
+    cases = [
+        # name, callable (all samples), serial callable (one sample), bytes per sample plane
+        ("embedding_00 96->128^3 (+mean)",
+         lambda: conv1x1.chain_samples_nhwc(emb0, feats, 93, gf=gf, out=out, want_mean=True),
+         lambda: conv1x1.chain_forward_nhwc(emb0, feats[:, 0], 93, gf=gf, out=out[:, 0]),
+         hw * (256 + 256 + 256 / spp)),
+        ("embedding_01 256->128^3 (+mean)",
+         lambda: conv1x1.chain_samples_nhwc(emb, feats, 128, prop=prop, out=out, want_mean=True),
+         lambda: conv1x1.chain_forward_nhwc(emb, feats[:, 0], 128, xb=prop, out=out[:, 0]),
+         hw * (256 + 256 + 2 * 256 / spp)),
+        ("kernel_regressor 256->128->128->441 (fp32 logits)",
+         lambda: conv1x1.chain_samples_nhwc(reg, feats, 128, prop=prop, regress=True, out=logits),
+         lambda: conv1x1.chain_forward_nhwc(reg, feats[:, 0], 128, xb=prop, out=one,
+                                            nhwc_out=False),
+         hw * (256 + 1764 + 256 / spp)),
+    ]
+    with th.no_grad():
+        for name, fused, serial, nbytes in cases:
+            ms_f, _, _ = timed(fused, a.warmup, a.steps)
+            ms_s, _, _ = timed(serial, a.warmup, a.steps)
+            per_plane = ms_f / spp
+            print(json.dumps({
+                "bench": "pipelined 1x1 chain " + name, "H": h, "W": w, "spp": spp,
+                "pipelined_ms_per_sample_plane": per_plane, "serial_round1_ms_per_sample_plane": ms_s,
+                "algorithmic_bytes_per_sample_plane": nbytes,
+                "hbm_bound_ms": nbytes / peak / 1e6, "frac_of_hbm_bound": nbytes / peak / 1e6 / per_plane,
+                "GBps": nbytes / per_plane / 1e6, "peak_GBps": peak}), flush=True)
+
+
+def bench_convs(a, dev):
+    """Every 3x3 convolution shape of the U-net (sbmc/modules.py:278-305) at the three
+    resolutions of a 720p image: csrc/conv3x3.cu (bias + activation fused) against
+    cuDNN bf16 channels_last + the separate bias / activation pass."""
+    from sbmc_b200 import conv3x3, unet_fast
+    import torch.nn.functional as F
+    h, w = a.h or 720, a.w or 1280
+    shapes = [(128, 128, 1), (384, 128, 1), (128, 256, 2), (256, 256, 2), (768, 256, 2),
+              (256, 512, 4), (512, 512, 4)]
+    total = {"own": 0.0, "cudnn": 0.0}
+    counts = {(128, 128, 1): 5, (384, 128, 1): 1, (128, 256, 2): 1, (256, 256, 2): 4,
+              (768, 256, 2): 1, (256, 512, 4): 1, (512, 512, 4): 2}
+    for cin, cout, div in shapes:
+        hh, ww = h // div, w // div
+        x = th.randn(1, hh, ww, cin, device=dev).to(th.bfloat16)
+        wt = (th.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5)).to(th.bfloat16)
+        bias = th.randn(cout, device=dev)
+        w9 = conv3x3.prepare_weight(wt)
+        y = th.empty(1, hh, ww, cout, device=dev, dtype=th.bfloat16)
+        xc = x.permute(0, 3, 1, 2)
+        wc = wt.contiguous(memory_format=th.channels_last)
+
+        def lib():
+            z = F.conv2d(xc, wc, None, 1, 1)
+            unet_fast._bias_act_(z, bias, 2)
+            return z
+        ms_o, _, _ = timed(lambda: conv3x3.conv3x3_nhwc(x, w9, bias, 2, out=y), a.warmup, a.steps)
+        ms_c, _, _ = timed(lib, a.warmup, a.steps)
+        ms_cc, _, _ = timed(lambda: F.conv2d(xc, wc, None, 1, 1), a.warmup, a.steps)
+        flops = 2.0 * hh * ww * cin * cout * 9
+        rel = ((y.permute(0, 3, 1, 2).float() - lib().float()).norm() / lib().float().norm()).item()
+        total["own"] += counts[(cin, cout, div)] * ms_o
+        total["cudnn"] += counts[(cin, cout, div)] * ms_c
+        print(json.dumps({
+            "bench": "conv3x3 %d->%d @ %dx%d" % (cin, cout, ww, hh), "own_ms": ms_o,
+            "cudnn_conv_plus_bias_act_ms": ms_c, "cudnn_conv_only_ms": ms_cc,
+            "own_TFLOPs": flops / ms_o / 1e9, "cudnn_conv_only_TFLOPs": flops / ms_cc / 1e9,
+            "convs_per_unet": counts[(cin, cout, div)], "rel_diff_vs_cudnn": rel}), flush=True)
+    print(json.dumps({"bench": "conv3x3: one U-net's 15 convolutions (sum of the above x counts)",
+                      "own_ms": total["own"], "cudnn_ms": total["cudnn"]}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["forward", "train", "chains"])
+    ap.add_argument("mode", choices=["forward", "train", "chains", "chains_v3", "convs"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--spp", type=int)
@@ -94,6 +187,10 @@ def main():
     th.manual_seed(0)
     if a.mode == "chains":
         return bench_chains(a, dev)
+    if a.mode == "chains_v3":
+        return bench_chains_v3(a, dev)
+    if a.mode == "convs":
+        return bench_convs(a, dev)
     if a.mode == "forward":
         bs, spp, h, w = a.bs or 1, a.spp or 4, a.h or 720, a.w or 1280
     else:

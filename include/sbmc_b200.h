@@ -88,7 +88,8 @@ SBMC_API int64_t sbmc_b200_launch_count(void);
 #define SBMC_KERNEL_CONV1X1 7      /* fused 3-layer 1x1 ConvChain (tcgen05)  */
 #define SBMC_KERNEL_TILES 8        /* tile reader: LZ4 inflate + assembly    */
 #define SBMC_KERNEL_OPTIM 9        /* fused gradient clipping + Adam         */
-#define SBMC_NUM_KERNEL_KINDS 10
+#define SBMC_KERNEL_CONV3X3 10     /* 3x3 implicit-GEMM convolution (tcgen05) */
+#define SBMC_NUM_KERNEL_KINDS 11
 SBMC_API int sbmc_b200_timing_enable(int flag);
 SBMC_API int sbmc_b200_timing_collect(double *ms_by_kind, int64_t *launches_by_kind);
 
@@ -183,6 +184,37 @@ SBMC_API int sbmc_conv1x1_chain_nhwc_bf16(const void *xa, int64_t a_img_stride, 
                                  int act, void *y, int64_t y_img_stride,
                                  int out_nhwc_bf16, int64_t n_img, int64_t hw,
                                  void *stream);
+
+/* The same chain for ALL SAMPLES of every pixel in one launch, software-pipelined
+ * (csrc/chain_v3.cu; reference: the per-sample loops of sbmc/models.py:143-181
+ * (embedding_XX + mean over spp) and :195-199 (kernel_regressor)).
+ * feats: bf16 [n][spp_total][hw][128] (f_img_stride / f_smp_stride elements between
+ * images / samples); prop: bf16 [n][hw][128] shared by the samples of a pixel, or
+ * NULL (then w1 is [128][128], else [128][256] with the feature channels first).
+ * Samples [sample0, sample0 + nsamples) are processed.
+ * regress == 0 (embedding; cout = n3p = 128): out bf16 [n][spp_total][hw][128]
+ *   (out_img_stride / out_smp_stride elements), and, when mean != NULL, mean over
+ *   the nsamples samples of the chain output (taken on the fp32 accumulators) as
+ *   bf16 (mean_f32 == 0) or fp32 [n][hw][128] -- models.py:181 `features.mean(1)`.
+ * regress != 0: out fp32 [n][spp_total][cout][hw] logits (fp32 accumulate + store),
+ *   mean must be NULL.  w3 bf16 [n3p][128], b3 fp32 [n3p], n3p multiple of 16. */
+SBMC_API int sbmc_chain_samples_nhwc_bf16(
+    const void *feats, int64_t f_img_stride, int64_t f_smp_stride, int64_t spp_total,
+    const void *prop, int64_t p_img_stride, const void *w1, const float *b1,
+    int64_t b1_img_stride, const void *w2, const float *b2, const void *w3, const float *b3,
+    int cout, int n3p, int act, int regress, void *out, int64_t out_img_stride,
+    int64_t out_smp_stride, void *mean, int64_t mean_img_stride, int mean_f32, int64_t n_img,
+    int64_t sample0, int64_t nsamples, int64_t hw, void *stream);
+
+/* 3x3 convolution, stride 1, zero padding 1 (the U-net convolutions of
+ * sbmc/modules.py:248-320) as an implicit GEMM on tcgen05 (csrc/conv3x3.cu):
+ * x bf16 [n][h][w][cin] (channels innermost), w9 bf16 [9][cout][cin] with tap
+ * index 3 * dy + dx (out[y][x] += w9[3 dy + dx] . x[y + dy - 1][x + dx - 1]),
+ * bias fp32 [cout]; y bf16 [n][h][w][cout] = act(conv + bias); act: 0 none,
+ * 1 ReLU, 2 LeakyReLU(0.01).  cin multiple of 64, cout multiple of 128. */
+SBMC_API int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *bias, void *y,
+                                    int64_t n, int h, int w, int cin, int cout, int act,
+                                    void *stream);
 
 /* U-net decoder glue (sbmc/modules.py:314-319): out = cat([bilinear_upsample(low,
  * size=(h, w), align_corners=False), skip], channels) in one pass on bf16

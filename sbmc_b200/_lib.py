@@ -39,6 +39,12 @@ SIGNATURES = {
     "sbmc_conv1x1_chain_nhwc_bf16":
         (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _int, _int,
                 _int, _ptr, _i64, _int, _i64, _i64, _ptr]),
+    "sbmc_chain_samples_nhwc_bf16":
+        (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr,
+                _int, _int, _int, _int, _ptr, _i64, _i64, _ptr, _i64, _int, _i64, _i64, _i64,
+                _i64, _ptr]),
+    "sbmc_conv3x3_nhwc_bf16":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_upsample_concat_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_bias_act_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _ptr]),
@@ -119,8 +125,8 @@ def last_path():
 
 
 KERNEL_KINDS = {0: "kw_fwd", 1: "kw_bwd_dweights", 2: "kw_bwd_ddata", 3: "s2g",
-                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain", 8: "tiles", 9: "optim"}
-NUM_KERNEL_KINDS = 10
+                4: "other", 5: "splat_fwd", 6: "splat_bwd", 7: "conv1x1_chain", 8: "tiles", 9: "optim", 10: "conv3x3"}
+NUM_KERNEL_KINDS = 11
 
 
 def timing_enable(flag):

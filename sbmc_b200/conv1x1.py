@@ -9,7 +9,8 @@ import torch as th
 
 from . import _lib
 
-__all__ = ["supports", "prepare", "chain_forward", "chain_forward_nhwc", "to_nhwc_bf16"]
+__all__ = ["supports", "prepare", "chain_forward", "chain_forward_nhwc", "chain_samples_nhwc",
+           "to_nhwc_bf16"]
 
 _HID = 128
 
@@ -259,3 +260,72 @@ def chain_forward_nhwc(chain, xa, ca, xb=None, gf=None, out=None, nhwc_out=True)
             1 if nhwc_out else 0, n, hw, th.cuda.current_stream(xa.device).cuda_stream)
     _lib.check(rc, "conv1x1_chain_nhwc")
     return out
+
+
+def chain_samples_nhwc(chain, feats, ca, prop=None, gf=None, out=None, want_mean=False,
+                       mean_dtype=th.bfloat16, regress=False, sample0=0, nsamples=None):
+    """The chain for all samples of every pixel in ONE pipelined launch
+    (csrc/chain_v3.cu; reference: the per-sample loops of sbmc/models.py:143-181 and
+    :195-199).
+
+    feats bf16 [n, spp, hw, 128] holding `ca` real channels per sample; prop bf16
+    [n, hw, 128] shared by the samples of a pixel (or None); gf [n, ngf] fp32 global
+    features (enter through a per-image first-layer bias).  Samples
+    [sample0, sample0 + nsamples) are processed.
+
+    regress=False (embedding chains): returns (out, mean) with out bf16
+    [n, spp, hw, 128] (only the processed samples are written) and, if want_mean,
+    mean [n, hw, 128] = the mean of the chain output over the processed samples,
+    taken on the fp32 accumulators (models.py:181), else None.
+    regress=True (kernel regressor): returns fp32 logits [n, nsamples, cout, hw]."""
+    n, spp, hw, _ = feats.shape
+    if feats.dtype != th.bfloat16 or feats.shape[-1] != _HID or feats.stride()[2:] != (_HID, 1):
+        raise RuntimeError("expected bf16 [n, spp, pixels, 128] features with contiguous samples")
+    nsamples = spp - sample0 if nsamples is None else nsamples
+    ngf = 0 if gf is None else gf.shape[1]
+    p = _prepare_nhwc(chain, ca, 0 if prop is None else _HID, ngf)
+    prop_t, p_img = (None, 0) if prop is None else _nhwc_view(prop)
+    if gf is not None:
+        b1 = (p.b1.unsqueeze(0) + gf.float().reshape(n, ngf) @ p.w1_gf.t()).contiguous()
+        b1_img = _HID
+    else:
+        b1, b1_img = p.b1, 0
+    f_img = feats.stride(0) if n > 1 else spp * hw * _HID
+    f_smp = feats.stride(1) if spp > 1 else hw * _HID
+    mean = None
+    if regress:
+        if want_mean:
+            raise RuntimeError("the regressor has no sample mean")
+        if out is None:
+            out = th.empty(n, nsamples, p.cout, hw, device=feats.device, dtype=th.float32)
+        if out.dtype != th.float32 or out.shape != (n, nsamples, p.cout, hw) \
+                or not out.is_contiguous():
+            raise RuntimeError("conv1x1 chain: bad fp32 logits tensor")
+        o_img, o_smp = nsamples * p.cout * hw, p.cout * hw
+        # the kernel indexes samples absolutely: shift the base by sample0 samples
+        o_ptr = out.data_ptr() - sample0 * o_smp * 4
+    else:
+        if p.cout != _HID:
+            raise RuntimeError("embedding chains must have 128 output channels")
+        if out is None:
+            out = feats.new_empty(n, spp, hw, _HID)
+        if out.dtype != th.bfloat16 or out.shape != (n, spp, hw, _HID) \
+                or out.stride()[2:] != (_HID, 1):
+            raise RuntimeError("conv1x1 chain: bad bf16 output tensor")
+        o_img = out.stride(0) if n > 1 else spp * hw * _HID
+        o_smp = out.stride(1) if spp > 1 else hw * _HID
+        o_ptr = out.data_ptr()
+        if want_mean:
+            mean = th.empty(n, hw, _HID, device=feats.device, dtype=mean_dtype)
+    lib = _lib.load()
+    with th.cuda.device(feats.device):
+        rc = lib.sbmc_chain_samples_nhwc_bf16(
+            feats.data_ptr(), f_img, f_smp, spp,
+            prop_t.data_ptr() if prop_t is not None else None, p_img,
+            p.w1.data_ptr(), b1.data_ptr(), b1_img, p.w2.data_ptr(), p.b2.data_ptr(),
+            p.w3.data_ptr(), p.b3.data_ptr(), p.cout, p.n3p, p.act, 1 if regress else 0,
+            o_ptr, o_img, o_smp, mean.data_ptr() if mean is not None else None, hw * _HID,
+            1 if (mean is not None and mean.dtype == th.float32) else 0, n, sample0, nsamples,
+            hw, th.cuda.current_stream(feats.device).cuda_stream)
+    _lib.check(rc, "chain_samples")
+    return out if regress else (out, mean)

@@ -1,0 +1,308 @@
+// conv3x3.cu -- 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on
+// tcgen05, bf16 channels-innermost activations, fp32 accumulation in TMEM, bias +
+// activation fused into the epilogue.
+//
+// Reference: the U-net of sbmc/modules.py:195-320 (`Autoencoder`: per level a
+// `left` and a `right` ConvChain of three 3x3 convolutions, modules.py:278-305) --
+// 88 % of the model's FLOPs.
+//
+// Formulation.  out[y][x][co] = bias[co] + sum_{dy,dx,ci} W[co][ci][dy][dx] *
+// in[y+dy-1][x+dx-1][ci].  For one of the nine taps this is a GEMM whose A operand
+// is the input shifted by (dy-1, dx-1).  A CTA owns an output tile of kRows = 2
+// image rows x 128 pixels (two M = 128 MMA row blocks) and kNT output channels:
+//
+//   * A.  For every 64-channel slab of the input ONE TMA box brings the tile plus
+//     its one-pixel halo -- 4 rows x 130 pixels x 64 channels, 128-byte swizzle --
+//     into shared memory; TMA's out-of-bounds zero fill IS the convolution's zero
+//     padding.  Pixels are the rows of the K-major operand (128 bytes each), so the
+//     operand of tap (dy, dx) for output row g is simply the 128 consecutive rows
+//     that start at halo row (g + dy) * 130 + dx: the nine taps are nine UMMA
+//     descriptors into the SAME resident slab (the swizzle pattern is a function of
+//     the shared-memory address, so a descriptor may start at any 128-byte row --
+//     checked on hardware by tools/umma_probe2.cu `shift`).  Every input element is
+//     fetched from L2 once per slab (x 1.07 halo) instead of nine times.
+//   * B.  Weights are prepared as [9][Cout][Cin] bf16; a stage is the
+//     (tap, 64-channel slab) block of 128 output channels (16 KB), streamed through a
+//     five-deep mbarrier ring by a second producer thread.
+//   * D.  fp32 accumulators in TMEM: kNT = 128 -> two row blocks x 128 columns,
+//     double-buffered so that the epilogue of tile i overlaps the main loop of tile
+//     i + 1; kNT = 256 -> two row blocks x two column halves = all 512 columns.
+//   * Epilogue (8 warps): tcgen05.ld -> + bias -> ReLU / LeakyReLU -> bf16 -> 64-byte
+//     vector stores, channels innermost.
+//
+// Warp roles: 0 = A producer, 1 = MMA issuer, 2 = TMEM allocation, 3 = B producer,
+// 4..11 = epilogue.
+#include <cuda_bf16.h>
+
+#include "umma.cuh"
+
+namespace sbmc {
+namespace c3 {
+
+constexpr int kSegPx = 128;
+constexpr int kRows = 2;
+constexpr int kHaloW = kSegPx + 2;
+constexpr int kHaloH = kRows + 2;
+constexpr int kASlab = kHaloH * kHaloW * 128;      // 66,560 bytes = 65 KB (1024-aligned)
+constexpr int kBStage = 128 * 128;                 // 128 output channels x 64 bf16
+constexpr int kStages = 5;
+constexpr int kThreads = 384;
+
+struct Args {
+  const float *bias;
+  __nv_bfloat16 *out;
+  int act;                 // 0 none, 1 ReLU, 2 LeakyReLU(0.01)
+  int H, W, Cin, Cout;
+  int tiles_x, tiles_y, n_img, n_tiles_n;
+  long long ntiles;
+};
+
+enum { B_AF = 0, B_AE = 2, B_BF = 4, B_BE = 4 + kStages, B_ACCF = 4 + 2 * kStages,
+       B_ACCE = 6 + 2 * kStages, B_COUNT = 8 + 2 * kStages };
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void stg128(void *p, const uint4 &v) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+struct TileCoord { int n, y0, x0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(long long tile, const Args &P, int nt) {
+  TileCoord t;
+  const int tx = (int)(tile % P.tiles_x); tile /= P.tiles_x;
+  const int ty = (int)(tile % P.tiles_y); tile /= P.tiles_y;
+  t.n = (int)(tile % P.n_img); tile /= P.n_img;
+  t.n0 = (int)tile * nt;
+  t.x0 = tx * kSegPx;
+  t.y0 = ty * kRows;
+  return t;
+}
+
+// NH: 128-column halves of the CTA's output-channel tile (1: kNT = 128, 2: kNT = 256).
+template <int NH>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W, H, N}
+               const __grid_constant__ CUtensorMap wmap,      // weights {Cin, Cout, 9}
+               const Args P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem;                               // 2 slabs
+  unsigned char *sB = smem + 2 * kASlab;                  // kStages stages
+  float *sBias = reinterpret_cast<float *>(sB + kStages * kBStage);   // NH * 128
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 256);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, (i >= B_ACCE) ? 8 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nslabs = P.Cin / 64;
+  constexpr int NT = NH * 128;
+
+  if (warp == 0) {
+    // ===================== A producer: halo slabs =====================
+    if (lane == 0) {
+      uint32_t ph = 0;          // bit ab
+      int ab = 0;
+      for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(tile, P, NT);
+        for (int s = 0; s < nslabs; ++s) {
+          mbar_wait(bars + B_AE + ab, ((ph >> ab) & 1) ^ 1); ph ^= 1u << ab;
+          mbar_expect_tx(bars + B_AF + ab, (uint32_t)kASlab);
+          tma_load_4d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, t.x0 - 1, t.y0 - 1, t.n);
+          ab ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: weight stages =====================
+    if (lane == 0) {
+      uint32_t ph = 0;          // bit st
+      int st = 0;
+      for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(tile, P, NT);
+        for (int s = 0; s < nslabs; ++s)
+          for (int tap = 0; tap < 9; ++tap)
+            for (int nh = 0; nh < NH; ++nh) {
+              mbar_wait(bars + B_BE + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
+              mbar_expect_tx(bars + B_BF + st, (uint32_t)kBStage);
+              tma_load_3d(sB + st * kBStage, &wmap, bars + B_BF + st, s * 64, t.n0 + nh * 128, tap);
+              st = (st + 1 == kStages) ? 0 : st + 1;
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      uint32_t ph_a = 0, ph_b = 0, ph_acc = 0;
+      int ab = 0, st = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+        const int buf = (NH == 1) ? (it & 1) : 0;
+        mbar_wait(bars + B_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
+        for (int s = 0; s < nslabs; ++s) {
+          mbar_wait(bars + B_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
+          const unsigned char *a_base = sA + ab * kASlab;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            for (int nh = 0; nh < NH; ++nh) {
+              mbar_wait(bars + B_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
+              tcgen05_fence_after();
+              const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kBStage);
+#pragma unroll
+              for (int g = 0; g < kRows; ++g) {
+                const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
+                const uint32_t d = tmem + ((NH == 1) ? buf * 256 + g * 128 : g * 256 + nh * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                            (s | tap | k) > 0);
+              }
+              umma_commit(bars + B_BE + st);
+              st = (st + 1 == kStages) ? 0 : st + 1;
+            }
+          }
+          umma_commit(bars + B_AE + ab);
+          ab ^= 1;
+        }
+        umma_commit(bars + B_ACCF + buf);
+      }
+      // drain: all commits have landed before the CTA exits
+      umma_commit(bars + B_AF);
+      mbar_wait(bars + B_AF, (ph_a & 1));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3, g = (warp - 4) >> 2;
+    const int px = quad * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t ph = 0;
+    int it = 0;
+    int cur_n0 = -1;
+    for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(tile, P, NT);
+      const int buf = (NH == 1) ? (it & 1) : 0;
+      if (t.n0 != cur_n0) {                 // bias of this channel tile (rarely changes)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = tid - 128; i < NT; i += 256) sBias[i] = P.bias[t.n0 + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_n0 = t.n0;
+      }
+      mbar_wait(bars + B_ACCF + buf, (ph >> buf) & 1); ph ^= 1u << buf;
+      tcgen05_fence_after();
+      const int y = t.y0 + g, x = t.x0 + px;
+      const bool valid = y < P.H && x < P.W;
+      __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + x) * P.Cout + t.n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        const uint32_t col = (NH == 1) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
+        float v[32];
+        tmem_ld_32x32b_x32(lane_base + col, v);
+        if (valid) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float u = v[8 * q4 + i] + sBias[c0 + 8 * q4 + i];
+              if (P.act == 1) u = fmaxf(u, 0.f);
+              else if (P.act == 2) u = fmaxf(u, 0.01f * u);
+              r[i] = u;
+            }
+            uint4 q;
+            q.x = pack_bf16(r[0], r[1]); q.y = pack_bf16(r[2], r[3]);
+            q.z = pack_bf16(r[4], r[5]); q.w = pack_bf16(r[6], r[7]);
+            stg128(dst + c0 + 8 * q4, q);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B_ACCE + buf);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+template <int NH>
+static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, cudaStream_t st) {
+  const size_t smem = (size_t)2 * kASlab + (size_t)kStages * kBStage + 256 * sizeof(float) +
+                      B_COUNT * sizeof(uint64_t) + 16;
+  auto kern = conv3x3_kernel<NH>;
+  SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
+  {
+    KernelTimer timer(SBMC_KERNEL_CONV3X3, st);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(am, wm, a);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  return SBMC_OK;
+}
+
+}  // namespace c3
+}  // namespace sbmc
+
+extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *bias, void *y,
+                                      int64_t n, int h, int w, int cin, int cout, int act,
+                                      void *stream) {
+  using namespace sbmc;
+  if (n < 0 || h < 1 || w < 1 || cin < 1 || cout < 1 || act < 0 || act > 2) {
+    set_error("conv3x3: invalid shape");
+    return SBMC_EINVAL;
+  }
+  if (n == 0) return SBMC_OK;
+  if (!x || !w9 || !bias || !y) {
+    set_error("conv3x3: null pointer argument");
+    return SBMC_EINVAL;
+  }
+  if (cin % 64 != 0 || cout % 128 != 0 || n >= (1ll << 31)) {
+    set_error("conv3x3: needs cin %% 64 == 0 and cout %% 128 == 0 (got %d, %d)", cin, cout);
+    return SBMC_EUNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+       reinterpret_cast<uintptr_t>(w9)) & 15) {
+    set_error("conv3x3: pointers must be 16-byte aligned");
+    return SBMC_EALIGN;
+  }
+  const int nh = (cout % 256 == 0) ? 2 : 1;
+  c3::Args a;
+  a.bias = bias; a.out = static_cast<__nv_bfloat16 *>(y); a.act = act;
+  a.H = h; a.W = w; a.Cin = cin; a.Cout = cout;
+  a.tiles_x = (w + c3::kSegPx - 1) / c3::kSegPx;
+  a.tiles_y = (h + c3::kRows - 1) / c3::kRows;
+  a.n_img = (int)n;
+  a.n_tiles_n = cout / (nh * 128);
+  a.ntiles = (long long)a.tiles_x * a.tiles_y * n * a.n_tiles_n;
+  CUtensorMap am, wm;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * w, (uint64_t)cin * 2 * w * h};
+    const uint32_t box[4] = {64, c3::kHaloW, c3::kHaloH, 1};
+    if (!encode_tensor_map_bf16_sw128(&am, x, 4, dims, str, box)) return SBMC_ECUDA;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};
+    const uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * cout};
+    const uint32_t box[3] = {64, 128, 1};
+    if (!encode_tensor_map_bf16_sw128(&wm, w9, 3, dims, str, box)) return SBMC_ECUDA;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  note_path(1);
+  return nh == 2 ? c3::launch<2>(a, am, wm, st) : c3::launch<1>(a, am, wm, st);
+}

@@ -193,6 +193,55 @@ bool encode_tensor_map_bf16_3d_sw128(CUtensorMap *map, const void *base, uint64_
   return true;
 }
 
+// bf16 tensor of any rank <= 5 with channels innermost, box {64, ...}, 128-byte
+// swizzle: every (64 channels x box[1] rows) slice of a box is one K-major UMMA
+// operand slab.  dims / box are innermost first; strides_bytes[i] is the stride of
+// dimension i + 1.
+bool encode_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank,
+                                  const uint64_t *dims, const uint64_t *strides_bytes,
+                                  const uint32_t *box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  if (rank < 2 || rank > 5 || box[0] != 64 || (reinterpret_cast<uintptr_t>(base) & 15)) {
+    set_error("tensor map (bf16 sw128): unsupported rank %d / box %u / base alignment", rank,
+              box[0]);
+    return false;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (dims[i] == 0 || dims[i] > (1ull << 32) || box[i] == 0 || box[i] > 256) {
+      set_error("tensor map (bf16 sw128): dim %d out of range (%llu, box %u)", i,
+                (unsigned long long)dims[i], box[i]);
+      return false;
+    }
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if ((strides_bytes[i] & 15) || strides_bytes[i] >= (1ull << 40)) {
+      set_error("tensor map (bf16 sw128): stride %d = %llu not encodable", i,
+                (unsigned long long)strides_bytes[i]);
+      return false;
+    }
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                  const_cast<void *>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 sw128, rank %d) failed with CUresult %d", rank,
+              (int)r);
+    return false;
+  }
+  return true;
+}
+
 }  // namespace sbmc
 
 extern "C" {

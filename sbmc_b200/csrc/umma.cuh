@@ -16,6 +16,10 @@ bool encode_tensor_map_bf16_3d_sw128(CUtensorMap *map, const void *base, uint64_
                                      uint64_t rows, uint64_t n, uint64_t img_stride,
                                      uint32_t box_rows);
 
+bool encode_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank,
+                                  const uint64_t *dims, const uint64_t *strides_bytes,
+                                  const uint32_t *box);
+
 #ifdef __CUDACC__
 
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a K-major

@@ -76,6 +76,12 @@ class Multisteps(nn.Module):
         # opt-in (inference): run the U-nets through cuDNN in bf16 / channels_last
         # (BASELINE.json config 3: "bf16 convs + fp32 splat")
         self.bf16_unet = False
+        # inside that pipeline: all samples of a step per launch on the pipelined
+        # tcgen05 chain kernel (csrc/chain_v3.cu) and the U-net convolutions on the
+        # tcgen05 implicit-GEMM kernel (csrc/conv3x3.cu); False selects the round-1
+        # serial chain kernel / cuDNN convolutions (A/B comparisons)
+        self.pipelined_chains = True
+        self.own_convs = True
 
         for step in range(nsteps):
             n_in = (n_features + n_global_features) if step == 0 \
@@ -190,22 +196,32 @@ class Multisteps(nn.Module):
         hw = h * w
         feats = _conv1x1.to_nhwc_bf16(features)              # [bs, spp, hw, 128]
         gf = gfeatures.reshape(bs, -1).float()
+        bf16_unet = getattr(self, "bf16_unet", False)
+        pipelined = getattr(self, "pipelined_chains", True)
         prop, ca = None, nf
         for step in range(self.nsteps):
             embed = getattr(self, "embedding_{:02d}".format(step))
-            new = feats.new_empty(bs, spp, hw, 128)
-            for sp in range(spp):
-                _conv1x1.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
-                                            gf=gf if step == 0 else None, out=new[:, sp])
+            if pipelined:
+                # all samples of the step in one launch; the sample mean (models.py:181)
+                # comes out of the same kernel, accumulated in fp32 by the tensor cores
+                new, reduced = _conv1x1.chain_samples_nhwc(
+                    embed, feats, ca, prop=prop, gf=gf if step == 0 else None, want_mean=True,
+                    mean_dtype=th.bfloat16 if bf16_unet else th.float32)
+            else:
+                new = feats.new_empty(bs, spp, hw, 128)
+                for sp in range(spp):
+                    _conv1x1.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
+                                                gf=gf if step == 0 else None, out=new[:, sp])
+                reduced = new.mean(1, dtype=th.float32)       # [bs, hw, 128]
+                if bf16_unet:
+                    reduced = reduced.to(th.bfloat16)
             feats, ca = new, 128
-            reduced = new.mean(1, dtype=th.float32)           # [bs, hw, 128]
-            if getattr(self, "bf16_unet", False):
-                reduced = reduced.to(th.bfloat16)
             x = reduced.view(bs, h, w, 128).permute(0, 3, 1, 2)   # NCHW, channels_last memory
             unet = getattr(self, "propagation_{:02d}".format(step))
-            if getattr(self, "bf16_unet", False) and _unet_fast.supports(unet):
-                y = _unet_fast.autoencoder_forward(unet, x)   # bf16 channels_last
-            elif getattr(self, "bf16_unet", False):
+            if bf16_unet and _unet_fast.supports(unet):
+                y = _unet_fast.autoencoder_forward(            # bf16 channels_last
+                    unet, x, own_convs=getattr(self, "own_convs", True))
+            elif bf16_unet:
                 with th.autocast("cuda", dtype=th.bfloat16):
                     y = unet(x)
             else:
@@ -214,12 +230,26 @@ class Multisteps(nn.Module):
 
         sum_r = sum_w = max_w = None
         k2 = self.ksize * self.ksize
-        for sp in range(spp):
-            kernels = _conv1x1.chain_forward_nhwc(
-                self.kernel_regressor, feats[:, sp], 128, xb=prop, nhwc_out=False)
-            kernels = kernels.view(bs, k2, h, w)
-            sum_r, sum_w, max_w = self.kernel_update(
-                crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
+        if pipelined:
+            # the regressor runs a few samples per launch (sample pairs share the `prop`
+            # operand and every weight chunk) so that the fp32 logits stay bounded
+            group = max(2, min(spp, int((4 << 30) // max(1, bs * k2 * hw * 4)) // 2 * 2))
+            for s0 in range(0, spp, group):
+                ns = min(group, spp - s0)
+                logits = _conv1x1.chain_samples_nhwc(self.kernel_regressor, feats, 128, prop=prop,
+                                                     regress=True, sample0=s0, nsamples=ns)
+                for i in range(ns):
+                    kernels = logits[:, i].view(bs, k2, h, w)
+                    sum_r, sum_w, max_w = self.kernel_update(
+                        crop_like(radiance[:, s0 + i], kernels), kernels, sum_r, sum_w, max_w)
+                del logits
+        else:
+            for sp in range(spp):
+                kernels = _conv1x1.chain_forward_nhwc(
+                    self.kernel_regressor, feats[:, sp], 128, xb=prop, nhwc_out=False)
+                kernels = kernels.view(bs, k2, h, w)
+                sum_r, sum_w, max_w = self.kernel_update(
+                    crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
         output = sum_r / (sum_w + self.eps)
         crop = (self.ksize - 1) // 2
         return {"radiance": output[..., crop:-crop, crop:-crop]}

@@ -1,14 +1,17 @@
 """bf16 channels_last inference path of the U-net (`modules.Autoencoder`,
-sbmc/modules.py:195-320): cuDNN runs the 3x3 convolutions (library GEMMs) on
-cached bf16 channels_last weights with the weight normalization folded in; the
-glue around them is ours -- bias + activation in one in-place pass and bilinear
-upsample + skip concatenation in one pass (csrc/unet_ops.cu) -- instead of eager
-PyTorch's broadcast add, activation, interpolate and cat kernels.
+sbmc/modules.py:195-320).  The 3x3 convolutions run on this repo's tcgen05
+implicit-GEMM kernel with bias + activation fused into its epilogue
+(csrc/conv3x3.cu, `own_convs=True`, the default) on cached bf16 weights with the
+weight normalization folded in; `own_convs=False` keeps the cuDNN library
+convolutions + the separate bias / activation pass (the comparison baseline).
+Bilinear upsample + skip concatenation is one pass (csrc/unet_ops.cu) instead of
+eager PyTorch's interpolate and cat kernels.
 """
 import torch as th
 import torch.nn.functional as F
 
 from . import _lib
+from . import conv3x3 as _conv3x3
 
 __all__ = ["supports", "autoencoder_forward"]
 
@@ -79,6 +82,22 @@ def _prepared(conv):
     return w, b
 
 
+def _prepared9(conv):
+    """(bf16 [9, cout, cin] tap-major weight with weight-norm folded, fp32 bias), cached."""
+    ver = tuple((p.data_ptr(), p._version) for p in conv.parameters())
+    cached = getattr(conv, "_sbmc_b200_fast9", None)
+    if cached is not None and cached[0] == ver:
+        return cached[1], cached[2]
+    if hasattr(conv, "weight_g") and hasattr(conv, "weight_v"):
+        w = th._weight_norm(conv.weight_v, conv.weight_g, 0)
+    else:
+        w = conv.weight
+    w9 = _conv3x3.prepare_weight(w)
+    b = conv.bias.detach().float().contiguous()
+    object.__setattr__(conv, "_sbmc_b200_fast9", (ver, w9, b))
+    return w9, b
+
+
 def _bias_act_(y, bias, act):
     n, c, h, w = y.shape
     lib = _lib.load()
@@ -89,8 +108,16 @@ def _bias_act_(y, bias, act):
     return y
 
 
-def _chain(chain, x):
+def _chain(chain, x, own_convs=True):
     for conv, act in _chain_layers(chain):
+        if own_convs and _conv3x3.supports_conv(conv):
+            # NCHW-shaped channels_last tensor <-> contiguous [n, h, w, c] view: no copies
+            w9, b = _prepared9(conv)
+            if not x.is_contiguous(memory_format=th.channels_last):
+                x = x.contiguous(memory_format=th.channels_last)
+            y = _conv3x3.conv3x3_nhwc(x.permute(0, 2, 3, 1), w9, b, act)
+            x = y.permute(0, 3, 1, 2)
+            continue
         w, b = _prepared(conv)
         x = F.conv2d(x, w, None, conv.stride, conv.padding)
         if not x.is_contiguous(memory_format=th.channels_last):
@@ -99,18 +126,18 @@ def _chain(chain, x):
     return x
 
 
-def _level(level, x):
+def _level(level, x, own_convs):
     from .modules import _upsample_concat
-    left = _chain(level.left, x)
+    left = _chain(level.left, x, own_convs)
     if level.is_last:
         return left
-    coarse = _level(level.next_level, level.downsample(left))
-    return _chain(level.right, _upsample_concat(coarse, left))
+    coarse = _level(level.next_level, level.downsample(left), own_convs)
+    return _chain(level.right, _upsample_concat(coarse, left), own_convs)
 
 
-def autoencoder_forward(autoencoder, x):
+def autoencoder_forward(autoencoder, x, own_convs=True):
     """x: [n, c, h, w] (any float dtype; converted to bf16 channels_last) ->
     bf16 channels_last [n, c_out, h, w].  Inference only."""
     x = x.to(th.bfloat16).contiguous(memory_format=th.channels_last)
     with th.no_grad():
-        return _level(autoencoder.net, x)
+        return _level(autoencoder.net, x, own_convs)

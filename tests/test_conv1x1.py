@@ -214,3 +214,93 @@ def test_to_nhwc_bf16_kernel_matches_torch():
         want = th.zeros(shape[:-3] + (h * w, 128), device="cuda", dtype=th.bfloat16)
         want[..., :c] = x.reshape(shape[:-3] + (c, h * w)).transpose(-1, -2)
         assert th.equal(got, want)
+
+
+# -- the pipelined all-samples kernel (csrc/chain_v3.cu) ---------------------------
+def _sample_inputs(name, n, spp, h, w, seed):
+    th.manual_seed(seed)
+    if name == "embedding_00":            # 93 features + 3 global features, no prop
+        f = th.randn(n, spp, 93, h, w, device="cuda")
+        gf = th.randn(n, 3, device="cuda")
+        return f, 93, None, gf
+    f = th.randn(n, spp, 128, h, w, device="cuda")
+    prop = th.randn(n, 128, h, w, device="cuda")
+    return f, 128, prop, None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["embedding_00", "embedding_01", "kernel_regressor"])
+@pytest.mark.parametrize("n,spp,hw", [(1, 1, (9, 13)), (2, 2, (16, 24)), (3, 3, (9, 13)),
+                                      (1, 4, (64, 128)), (2, 5, (20, 36))])
+def test_pipelined_chain_matches_the_serial_kernel_and_fp32(name, n, spp, hw):
+    """All samples in one launch (two streams in lock step, hidden activations in
+    tensor memory, sample mean accumulated by the tensor cores) against the serial
+    per-sample kernel (same rounding points) and the fp32 module."""
+    chain = _chains()[name].cuda().eval()
+    with th.no_grad():
+        for prm in chain.parameters():
+            prm.add_(0.05 * th.randn_like(prm))
+    h, w = hw
+    f, ca, prop, gf = _sample_inputs(name, n, spp, h, w, 11)
+    feats = conv1x1.to_nhwc_bf16(f)                                   # [n, spp, hw, 128]
+    prop_n = None if prop is None else conv1x1.to_nhwc_bf16(prop)
+    regress = name == "kernel_regressor"
+    with th.no_grad():
+        if regress:
+            got = conv1x1.chain_samples_nhwc(chain, feats, ca, prop=prop_n, regress=True)
+            assert got.shape == (n, spp, 441, h * w) and got.dtype == th.float32
+        else:
+            got, mean = conv1x1.chain_samples_nhwc(chain, feats, ca, prop=prop_n, gf=gf,
+                                                   want_mean=True, mean_dtype=th.float32)
+            assert got.shape == (n, spp, h * w, 128) and mean.shape == (n, h * w, 128)
+        acc = 0
+        for s in range(spp):
+            one = conv1x1.chain_forward_nhwc(chain, feats[:, s], ca, xb=prop_n, gf=gf,
+                                             nhwc_out=not regress)
+            ctx = prop if prop is not None else gf.view(n, 3, 1, 1).expand(n, 3, h, w)
+            ref = chain(th.cat([f[:, s], ctx], 1))
+            if regress:
+                g = got[:, s]
+                assert ((g - one).norm() / one.norm()).item() < 1e-5     # same rounding points
+                g = g.view(n, 441, h, w)
+            else:
+                g = got[:, s].float()
+                assert ((g - one.float()).norm() / one.float().norm()).item() < 2e-3
+                g = g.view(n, h, w, 128).permute(0, 3, 1, 2)
+                acc = acc + ref
+            assert ((g - ref).norm() / ref.norm()).item() < 2e-2
+        if not regress:
+            want = (acc / spp).permute(0, 2, 3, 1).reshape(n, h * w, 128)
+            assert ((mean - want).norm() / want.norm()).item() < 2e-2
+            # the mean is taken on the fp32 accumulators: at least as close to the fp32
+            # module as the mean of the bf16-rounded outputs
+            e_fused = (mean - want).norm().item()
+            e_round = (got.float().mean(1) - want).norm().item()
+            assert e_fused <= 1.05 * e_round + 1e-6
+
+
+@pytest.mark.gpu
+def test_pipelined_chain_sample_ranges_and_bf16_mean():
+    """Sample sub-ranges (the regressor is run a few samples at a time to bound the
+    logits buffer) and the bf16 mean output."""
+    chains = _chains()
+    reg = chains["kernel_regressor"].cuda().eval()
+    emb = chains["embedding_01"].cuda().eval()
+    n, spp, h, w = 2, 5, 12, 20
+    f, ca, prop, _ = _sample_inputs("kernel_regressor", n, spp, h, w, 12)
+    feats, prop_n = conv1x1.to_nhwc_bf16(f), conv1x1.to_nhwc_bf16(prop)
+    with th.no_grad():
+        full = conv1x1.chain_samples_nhwc(reg, feats, ca, prop=prop_n, regress=True)
+        a = conv1x1.chain_samples_nhwc(reg, feats, ca, prop=prop_n, regress=True, sample0=0,
+                                       nsamples=2)
+        b = conv1x1.chain_samples_nhwc(reg, feats, ca, prop=prop_n, regress=True, sample0=2,
+                                       nsamples=3)
+        assert th.equal(th.cat([a, b], 1), full)
+        out = th.zeros(n, spp, h * w, 128, device="cuda", dtype=th.bfloat16)
+        _, m16 = conv1x1.chain_samples_nhwc(emb, feats, ca, prop=prop_n, out=out, want_mean=True,
+                                            sample0=1, nsamples=3)
+        o32, m32 = conv1x1.chain_samples_nhwc(emb, feats, ca, prop=prop_n, want_mean=True,
+                                              mean_dtype=th.float32, sample0=1, nsamples=3)
+        assert (out[:, 0] == 0).all() and (out[:, 4] == 0).all()
+        assert th.equal(out[:, 1:4], o32[:, 1:4])
+        assert m16.dtype == th.bfloat16 and th.equal(m16, m32.to(th.bfloat16))

@@ -1,0 +1,67 @@
+"""3x3 implicit-GEMM convolution (csrc/conv3x3.cu) against torch's fp32 conv2d on the
+same bf16-rounded operands (tight: only the fp32 accumulation order differs) and the
+U-net fast path built on it against the fp32 module."""
+import pytest
+import torch as th
+import torch.nn.functional as F
+
+from sbmc_b200 import conv3x3, modules, unet_fast
+
+
+def test_prepare_weight_layout():
+    w = th.randn(128, 64, 3, 3)
+    w9 = conv3x3.prepare_weight(w)
+    assert w9.shape == (9, 128, 64) and w9.dtype == th.bfloat16
+    assert th.equal(w9[3 * 2 + 1], w[:, :, 2, 1].to(th.bfloat16))
+    assert conv3x3.supports_conv(th.nn.Conv2d(128, 256, 3, padding=1))
+    assert not conv3x3.supports_conv(th.nn.Conv2d(100, 256, 3, padding=1))
+    assert not conv3x3.supports_conv(th.nn.Conv2d(128, 256, 3, padding=0))
+    assert not conv3x3.supports_conv(th.nn.Conv2d(128, 256, 5, padding=2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", [(128, 128), (64, 256), (384, 128), (256, 512)])
+@pytest.mark.parametrize("n,h,w", [(1, 8, 128), (2, 7, 45), (1, 33, 300), (3, 2, 129)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_conv3x3_matches_torch(cin, cout, n, h, w, act):
+    th.manual_seed(cin + cout + h + w)
+    x = th.randn(n, h, w, cin, device="cuda").to(th.bfloat16)
+    wt = (th.randn(cout, cin, 3, 3, device="cuda") / (3 * cin ** 0.5)).to(th.bfloat16)
+    bias = th.randn(cout, device="cuda")
+    got = conv3x3.conv3x3_nhwc(x, conv3x3.prepare_weight(wt), bias, act=act)
+    assert got.shape == (n, h, w, cout) and got.dtype == th.bfloat16
+    prev = th.backends.cudnn.allow_tf32
+    th.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    finally:
+        th.backends.cudnn.allow_tf32 = prev
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.01)
+    ref = ref.permute(0, 2, 3, 1)
+    err = (got.float() - ref).abs()
+    scale = ref.abs().max().item()
+    # bf16 output rounding: half an ulp = 2^-9 relative
+    assert err.max().item() <= 6e-3 * scale
+    assert ((got.float() - ref).norm() / ref.norm()).item() < 3e-3
+
+
+@pytest.mark.gpu
+def test_unet_fast_path_with_own_convs_matches_fp32_module():
+    th.manual_seed(0)
+    net = modules.Autoencoder(128, 128, num_levels=3, increase_factor=2.0, num_convs=3,
+                              width=128, ksize=3, output_type="leaky_relu", pooling="max").cuda().eval()
+    x = th.randn(2, 128, 40, 72, device="cuda")
+    prev = th.backends.cudnn.allow_tf32
+    th.backends.cudnn.allow_tf32 = False
+    try:
+        with th.no_grad():
+            ref = net(x)
+            lib = unet_fast.autoencoder_forward(net, x, own_convs=False).float()
+            got = unet_fast.autoencoder_forward(net, x, own_convs=True).float()
+    finally:
+        th.backends.cudnn.allow_tf32 = prev
+    assert got.shape == ref.shape
+    e_own = ((got - ref).norm() / ref.norm()).item()
+    e_lib = ((lib - ref).norm() / ref.norm()).item()
+    assert e_own < 3e-2 and e_own < 1.5 * e_lib + 1e-3

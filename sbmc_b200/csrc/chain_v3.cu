@@ -62,7 +62,21 @@ struct Args {
   int s0, ns;                             // samples [s0, s0 + ns) of the feature tensor
   int hw, tiles_per_img;
   long long ntiles;
+  long long *trace;                       // developer timeline (SBMC_CHAIN_TRACE builds), or null
 };
+
+// Developer timeline: CTA 0 appends (code, clock) pairs; compiled out by default.
+#ifdef SBMC_CHAIN_TRACE
+__device__ __forceinline__ void trace_ev(const Args &P, int code) {
+  if (P.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long *>(P.trace), 1ull);
+    if (i < 8000) { P.trace[2 + 2 * i] = code; P.trace[3 + 2 * i] = clock64(); }
+  }
+}
+#define TRACE(code) trace_ev(P, code)
+#else
+#define TRACE(code) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -204,6 +218,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
         for (int j = 0; j < npairs; ++j) {
           const bool bvalid = 2 * j + 1 < P.ns;
           mbar_wait(bars + B_F_EMPTY, ph_fe ^ 1); ph_fe ^= 1;
+          TRACE(1);                                   // F slot free, loads issued
           mbar_expect_tx(bars + B_F_FULL, (uint32_t)((bvalid ? 4 : 2) * kSlab));
           for (int e = 0; e < (bvalid ? 2 : 1); ++e)
             for (int kb = 0; kb < 2; ++kb)
@@ -256,11 +271,14 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
           const int ne = (2 * j + 1 < P.ns) ? 2 : 1;
           const bool last = j == npairs - 1;
           // ---- layer 1: X_e = [F_e | P] . W1^T  (operands in shared memory) ----
+          TRACE(10);
           mbar_wait(bars + B_F_FULL, ph_f); ph_f ^= 1;
           if (KS1 == 4 && j == 0) { mbar_wait(bars + B_P_FULL, ph_p); ph_p ^= 1; }
+          TRACE(11);                                  // F (and P) landed
           for (int e = 0; e < ne; ++e) {
             if ((has_prev >> e) & 1) wait_ar(e);      // X_e drained by the previous item
             has_prev |= 1u << e;
+            TRACE(12 + e);                            // X_e free, issuing layer 1
             tcgen05_fence_after();
             const uint32_t x = tmem + e * 192;
 #pragma unroll
@@ -278,6 +296,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
           // ---- layer 2: X_e = Y_e . W2^T  (A operand in tensor memory) ----
           for (int e = 0; e < ne; ++e) {
             wait_ar(e);
+            TRACE(14 + e);                            // E1_e done, issuing layer 2
             tcgen05_fence_after();
             const uint32_t x = tmem + e * 192, y = x + 128;
 #pragma unroll
@@ -292,6 +311,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
             if (do_mean && j == 0) { mbar_wait(bars + B_M_EMPTY, ph_me ^ 1); ph_me ^= 1; }
             for (int e = 0; e < ne; ++e) {
               wait_ar(e);
+              TRACE(16 + e);                          // E2_e done, issuing layer 3
               tcgen05_fence_after();
               const uint32_t x = tmem + e * 192, y = x + 128;
 #pragma unroll
@@ -365,15 +385,18 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(bars + B_ACC0 + e, ph_acc); ph_acc ^= 1;
+          if (wi == 0 && lane == 0) TRACE(20 + 10 * e + 2 * layer);       // accumulator ready
           tcgen05_fence_after();
           hidden_epilogue<LEAKY>(x, y, layer ? sB2 : sb1, half);
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bars + B_AR0 + e);
+          if (wi == 0 && lane == 0) TRACE(21 + 10 * e + 2 * layer);       // epilogue done
         }
         if (!REGRESS) {
           // ---- embedding output: bf16, channels innermost ----
           mbar_wait(bars + B_ACC0 + e, ph_acc); ph_acc ^= 1;
+          if (wi == 0 && lane == 0) TRACE(24 + 10 * e);
           tcgen05_fence_after();
           __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(P.out) + n * P.out_img +
                                (long long)(P.s0 + sl) * P.out_smp + p * kHid + half * 64;
@@ -399,6 +422,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bars + B_AR0 + e);
+          if (wi == 0 && lane == 0) TRACE(25 + 10 * e);
           // ---- mean over the samples: read once per tile by the last stream ----
           if (do_mean && sl == P.ns - 1) {
             mbar_wait(bars + B_M_FULL, ph_m); ph_m ^= 1;
@@ -454,15 +478,28 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
             if (half * 32 < rows) {                   // warp-uniform
               float v[32];
               tmem_ld_32x32b_x32(o + half * 32, v);
-              if (valid) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 b = __ldg(reinterpret_cast<const float4 *>(P.b3 + col + 4 * g));
-                  const int cc = col + 4 * g;
-                  if (cc + 0 < P.cout) stg32_stream(yp + (long long)(cc + 0) * P.hw, v[4 * g + 0] + b.x);
-                  if (cc + 1 < P.cout) stg32_stream(yp + (long long)(cc + 1) * P.hw, v[4 * g + 1] + b.y);
-                  if (cc + 2 < P.cout) stg32_stream(yp + (long long)(cc + 2) * P.hw, v[4 * g + 2] + b.z);
-                  if (cc + 3 < P.cout) stg32_stream(yp + (long long)(cc + 3) * P.hw, v[4 * g + 3] + b.w);
+              for (int g = 0; g < 8; ++g) {           // + bias (uniform 128-bit loads)
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(P.b3 + col + 4 * g));
+                v[4 * g + 0] += b.x; v[4 * g + 1] += b.y;
+                v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+              }
+              if (valid) {
+                // one running pointer, one add per store; the channel bound is tested
+                // per 32-channel block (warp-uniform), not per store
+                float *ptr = yp + (long long)col * P.hw;
+                if (col + 32 <= P.cout) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    stg32_stream(ptr, v[i]);
+                    ptr += P.hw;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    if (col + i < P.cout) stg32_stream(ptr, v[i]);
+                    ptr += P.hw;
+                  }
                 }
               }
             }
@@ -506,6 +543,10 @@ static int launch(const Args &a, const CUtensorMap &fm, const CUtensorMap &pm,
 }  // namespace v3
 }  // namespace sbmc
 
+#ifdef SBMC_CHAIN_TRACE
+extern "C" __attribute__((visibility("default"))) void *sbmc_b200_debug_pointer = nullptr;
+#endif
+
 // Public entry point (include/sbmc_b200.h).
 extern "C" int sbmc_chain_samples_nhwc_bf16(
     const void *feats, int64_t f_img_stride, int64_t f_smp_stride, int64_t spp_total,
@@ -540,6 +581,10 @@ extern "C" int sbmc_chain_samples_nhwc_bf16(
   a.hw = (int)hw;
   a.tiles_per_img = (int)((hw + v3::kTileP - 1) / v3::kTileP);
   a.ntiles = (long long)a.tiles_per_img * n_img;
+  a.trace = nullptr;
+#ifdef SBMC_CHAIN_TRACE
+  a.trace = static_cast<long long *>(sbmc_b200_debug_pointer);
+#endif
   CUtensorMap fm, pm, m1, m2, m3;
   {
     const uint64_t dims[4] = {128, (uint64_t)hw, (uint64_t)spp_total, (uint64_t)n_img};

@@ -22,16 +22,20 @@
 //     checked on hardware by tools/umma_probe2.cu `shift`).  Every input element is
 //     fetched from L2 once per slab (x 1.07 halo) instead of nine times.
 //   * B.  Weights are prepared as [9][Cout][Cin] bf16; a stage is the
-//     (tap, 64-channel slab) block of 128 output channels (16 KB), streamed through a
-//     five-deep mbarrier ring by a second producer thread.
-//   * D.  fp32 accumulators in TMEM: kNT = 128 -> two row blocks x 128 columns,
+//     (tap, 64-channel slab) block of NT output channels (NT = 128: 16 KB, six-deep
+//     mbarrier ring; NT = 256: 32 KB, three-deep), streamed by a second producer
+//     thread.  NT = 256 whenever Cout allows: one MMA then covers 128 pixels x 256
+//     channels and the A rows are read from shared memory once per 256 outputs --
+//     with N = 128 the operand reads alone (A 4 KB + B 4 KB per 64-cycle MMA) use the
+//     whole 128 B/clk of shared-memory bandwidth (profiles/r2c_ncu.md).
+//   * D.  fp32 accumulators in TMEM: NT = 128 -> two row blocks x 128 columns,
 //     double-buffered so that the epilogue of tile i overlaps the main loop of tile
-//     i + 1; kNT = 256 -> two row blocks x two column halves = all 512 columns.
-//   * Epilogue (8 warps): tcgen05.ld -> + bias -> ReLU / LeakyReLU -> bf16 -> 64-byte
+//     i + 1; NT = 256 -> two row blocks x 256 columns = all 512 columns.
+//   * Epilogue (16 warps): tcgen05.ld -> + bias -> ReLU / LeakyReLU -> bf16 -> 64-byte
 //     vector stores, channels innermost.
 //
 // Warp roles: 0 = A producer, 1 = MMA issuer, 2 = TMEM allocation, 3 = B producer,
-// 4..11 = epilogue.
+// 4..19 = epilogue.
 #include <cuda_bf16.h>
 
 #include "umma.cuh"
@@ -44,9 +48,10 @@ constexpr int kRows = 2;
 constexpr int kHaloW = kSegPx + 2;
 constexpr int kHaloH = kRows + 2;
 constexpr int kASlab = kHaloH * kHaloW * 128;      // 66,560 bytes = 65 KB (1024-aligned)
-constexpr int kBStage = 128 * 128;                 // 128 output channels x 64 bf16
-constexpr int kStages = 5;
-constexpr int kThreads = 384;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 32 * (4 + kEpiWarps);
+constexpr int kMaxStages = 6;
+__host__ __device__ constexpr int stages_for(int nt) { return nt == 128 ? 6 : 3; }
 
 struct Args {
   const float *bias;
@@ -57,8 +62,8 @@ struct Args {
   long long ntiles;
 };
 
-enum { B_AF = 0, B_AE = 2, B_BF = 4, B_BE = 4 + kStages, B_ACCF = 4 + 2 * kStages,
-       B_ACCE = 6 + 2 * kStages, B_COUNT = 8 + 2 * kStages };
+enum { B_AF = 0, B_AE = 2, B_BF = 4, B_BE = 4 + kMaxStages, B_ACCF = 4 + 2 * kMaxStages,
+       B_ACCE = 6 + 2 * kMaxStages, B_COUNT = 8 + 2 * kMaxStages };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -85,23 +90,24 @@ __device__ __forceinline__ TileCoord tile_coord(long long tile, const Args &P, i
   return t;
 }
 
-// NH: 128-column halves of the CTA's output-channel tile (1: kNT = 128, 2: kNT = 256).
-template <int NH>
+// NT: output channels per CTA tile = MMA N (128 or 256).
+template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W, H, N}
                const __grid_constant__ CUtensorMap wmap,      // weights {Cin, Cout, 9}
                const Args P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sA = smem;                               // 2 slabs
+  constexpr int kStages = stages_for(NT);
+  constexpr int kBStage = NT * 128;                       // NT output channels x 64 bf16
   unsigned char *sB = smem + 2 * kASlab;                  // kStages stages
-  float *sBias = reinterpret_cast<float *>(sB + kStages * kBStage);   // NH * 128
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 256);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kStages * kBStage);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, (i >= B_ACCE) ? 8 : 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, (i >= B_ACCE) ? kEpiWarps : 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -110,7 +116,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int nslabs = P.Cin / 64;
-  constexpr int NT = NH * 128;
 
   if (warp == 0) {
     // ===================== A producer: halo slabs =====================
@@ -135,45 +140,42 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, P, NT);
         for (int s = 0; s < nslabs; ++s)
-          for (int tap = 0; tap < 9; ++tap)
-            for (int nh = 0; nh < NH; ++nh) {
-              mbar_wait(bars + B_BE + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
-              mbar_expect_tx(bars + B_BF + st, (uint32_t)kBStage);
-              tma_load_3d(sB + st * kBStage, &wmap, bars + B_BF + st, s * 64, t.n0 + nh * 128, tap);
-              st = (st + 1 == kStages) ? 0 : st + 1;
-            }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bars + B_BE + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
+            mbar_expect_tx(bars + B_BF + st, (uint32_t)kBStage);
+            tma_load_3d(sB + st * kBStage, &wmap, bars + B_BF + st, s * 64, t.n0, tap);
+            st = (st + 1 == kStages) ? 0 : st + 1;
+          }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t idesc = umma_idesc_bf16(128, NT);
       uint32_t ph_a = 0, ph_b = 0, ph_acc = 0;
       int ab = 0, st = 0, it = 0;
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-        const int buf = (NH == 1) ? (it & 1) : 0;
+        const int buf = (NT == 128) ? (it & 1) : 0;
         mbar_wait(bars + B_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + B_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
           const unsigned char *a_base = sA + ab * kASlab;
           for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3, dx = tap - 3 * dy;
-            for (int nh = 0; nh < NH; ++nh) {
-              mbar_wait(bars + B_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
-              tcgen05_fence_after();
-              const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kBStage);
+            mbar_wait(bars + B_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
+            tcgen05_fence_after();
+            const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kBStage);
 #pragma unroll
-              for (int g = 0; g < kRows; ++g) {
-                const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
-                const uint32_t d = tmem + ((NH == 1) ? buf * 256 + g * 128 : g * 256 + nh * 128);
+            for (int g = 0; g < kRows; ++g) {
+              const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
+              const uint32_t d = tmem + ((NT == 128) ? buf * 256 + g * 128 : g * 256);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
-                            (s | tap | k) > 0);
-              }
-              umma_commit(bars + B_BE + st);
-              st = (st + 1 == kStages) ? 0 : st + 1;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                          (s | tap | k) > 0);
             }
+            umma_commit(bars + B_BE + st);
+            st = (st + 1 == kStages) ? 0 : st + 1;
           }
           umma_commit(bars + B_AE + ab);
           ab ^= 1;
@@ -186,38 +188,36 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3, g = (warp - 4) >> 2;
+    // warp -> (lane quadrant, row block g, column half): 4 x 2 x 2 = 16 warps
+    const int quad = warp & 3, g = ((warp - 4) >> 2) & 1, part = (warp - 4) >> 3;
     const int px = quad * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t ph = 0;
     int it = 0;
-    int cur_n0 = -1;
     for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const TileCoord t = tile_coord(tile, P, NT);
-      const int buf = (NH == 1) ? (it & 1) : 0;
-      if (t.n0 != cur_n0) {                 // bias of this channel tile (rarely changes)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = tid - 128; i < NT; i += 256) sBias[i] = P.bias[t.n0 + i];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_n0 = t.n0;
-      }
+      const int buf = (NT == 128) ? (it & 1) : 0;
       mbar_wait(bars + B_ACCF + buf, (ph >> buf) & 1); ph ^= 1u << buf;
       tcgen05_fence_after();
       const int y = t.y0 + g, x = t.x0 + px;
       const bool valid = y < P.H && x < P.W;
       __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + x) * P.Cout + t.n0;
+      const float *bias = P.bias + t.n0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        const uint32_t col = (NH == 1) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
+      for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 32) {
+        const uint32_t col = (NT == 128) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
         float v[32];
         tmem_ld_32x32b_x32(lane_base + col, v);
         if (valid) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * q4));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * q4 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float r[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float u = v[8 * q4 + i] + sBias[c0 + 8 * q4 + i];
+              float u = v[8 * q4 + i] + bb[i];
               if (P.act == 1) u = fmaxf(u, 0.f);
               else if (P.act == 2) u = fmaxf(u, 0.01f * u);
               r[i] = u;
@@ -239,11 +239,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-template <int NH>
+template <int NT>
 static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, cudaStream_t st) {
-  const size_t smem = (size_t)2 * kASlab + (size_t)kStages * kBStage + 256 * sizeof(float) +
+  const size_t smem = (size_t)2 * kASlab + (size_t)stages_for(NT) * NT * 128 +
                       B_COUNT * sizeof(uint64_t) + 16;
-  auto kern = conv3x3_kernel<NH>;
+  auto kern = conv3x3_kernel<NT>;
   SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   {
@@ -280,14 +280,14 @@ extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float
     set_error("conv3x3: pointers must be 16-byte aligned");
     return SBMC_EALIGN;
   }
-  const int nh = (cout % 256 == 0) ? 2 : 1;
+  const int nt = (cout % 256 == 0) ? 256 : 128;
   c3::Args a;
   a.bias = bias; a.out = static_cast<__nv_bfloat16 *>(y); a.act = act;
   a.H = h; a.W = w; a.Cin = cin; a.Cout = cout;
   a.tiles_x = (w + c3::kSegPx - 1) / c3::kSegPx;
   a.tiles_y = (h + c3::kRows - 1) / c3::kRows;
   a.n_img = (int)n;
-  a.n_tiles_n = cout / (nh * 128);
+  a.n_tiles_n = cout / nt;
   a.ntiles = (long long)a.tiles_x * a.tiles_y * n * a.n_tiles_n;
   CUtensorMap am, wm;
   {
@@ -299,10 +299,10 @@ extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float
   {
     const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};
     const uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * cout};
-    const uint32_t box[3] = {64, 128, 1};
+    const uint32_t box[3] = {64, (uint32_t)nt, 1};
     if (!encode_tensor_map_bf16_sw128(&wm, w9, 3, dims, str, box)) return SBMC_ECUDA;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   note_path(1);
-  return nh == 2 ? c3::launch<2>(a, am, wm, st) : c3::launch<1>(a, am, wm, st);
+  return nt == 256 ? c3::launch<256>(a, am, wm, st) : c3::launch<128>(a, am, wm, st);
 }

@@ -20,9 +20,17 @@ _GRAD_CLIP = 1000
 
 class SampleBasedDenoiserInterface(object):
     """model: nn.Module taking / returning dicts; lr: Adam step size; cuda: move
-    the model (and every batch) to the GPU; fused_optimizer: see below."""
+    the model (and every batch) to the GPU; fused_optimizer: see below;
+    allow_tf32: the reference trains in fp32 (PyTorch 1.2 had no TF32), so the
+    cuDNN / cuBLAS TF32 paths PyTorch enables by default for convolutions are
+    switched OFF unless asked for -- the policy is set here, explicitly, and
+    logged."""
 
-    def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False):
+    def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False, allow_tf32=False):
+        self.allow_tf32 = bool(allow_tf32)
+        th.backends.cudnn.allow_tf32 = self.allow_tf32
+        th.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+        LOG.info("fp32 convolution policy: TF32 %s", "allowed" if self.allow_tf32 else "off")
         self.model = model.cuda() if cuda else model
         self.device = "cuda" if cuda else "cpu"
         self.loss_fn = losses.TonemappedRelativeMSE()
@@ -68,12 +76,15 @@ class SampleBasedDenoiserInterface(object):
             norm = self.optimizer.last_grad_norm[0]
         else:
             norm = th.nn.utils.clip_grad_norm_(self.model.parameters(), _GRAD_CLIP)
-        if norm > _GRAD_CLIP:
-            LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, float(norm))
-        if not self.fused_optimizer:
             self.optimizer.step()
+        # the gradient norm is only logged: it is read together with the rmse in ONE
+        # device-to-host transfer after the optimizer has been launched (no extra
+        # synchronisation between the clip and the Adam kernels)
         with th.no_grad():
-            rmse = self.rmse_fn(out, tgt).item()
+            rmse, norm = th.stack([self.rmse_fn(out, tgt).float().reshape(()),
+                                   norm.float().reshape(()).to(out.device)]).tolist()
+        if norm > _GRAD_CLIP:
+            LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, norm)
         return {"loss": value, "rmse": rmse}
 
     def init_validation(self):

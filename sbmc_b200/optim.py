@@ -49,6 +49,13 @@ def _backend():
     return _CudaBackend()
 
 
+def _bump_version(p):
+    try:
+        th.autograd.graph.increment_version(p)
+    except (AttributeError, RuntimeError):
+        p.add_(0)                                 # in-place no-op: same effect
+
+
 class FusedAdam(th.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
@@ -137,4 +144,8 @@ class FusedAdam(th.optim.Optimizer):
                              group["eps"], 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t))
                 for r in part:
                     self.state[r[0]]["step"] += 1
+                    # the kernel wrote through raw pointers: bump the autograd version
+                    # counter so that caches keyed on it (conv1x1.prepare, unet_fast)
+                    # see the update
+                    _bump_version(r[0])
         return loss

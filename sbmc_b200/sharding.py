@@ -462,26 +462,32 @@ def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None
     hw = rows_ext * w
     prop, ca = None, nf
     utop, ubot = uplan.halo_top(rank), uplan.halo_bot(rank)
+    own_convs = getattr(model, "own_convs", True)
     for step in range(model.nsteps):
         embed = getattr(model, "embedding_{:02d}".format(step))
-        new = feats.new_empty(bs, spp, hw, 128)
-        for sp in range(spp):
-            _c.chain_forward_nhwc(embed, feats[:, sp], ca, xb=prop,
-                                  gf=gf if step == 0 else None, out=new[:, sp])
+        # all samples in one launch; the sample mean comes out of the same kernel
+        new, reduced = _c.chain_samples_nhwc(embed, feats, ca, prop=prop,
+                                             gf=gf if step == 0 else None, want_mean=True)
         feats, ca = new, 128
-        reduced = new.mean(1, dtype=th.float32).to(th.bfloat16)    # [bs, hw, 128]
         band = reduced.view(bs, rows_ext, w * 128)[:, top:top + rows]
         ext = exchange_halo(uplan, rank, band, group)              # [bs, utop+rows+ubot, w*128]
         x = ext.view(bs, utop + rows + ubot, w, 128).permute(0, 3, 1, 2)
-        y = _u.autoencoder_forward(getattr(model, "propagation_{:02d}".format(step)), x)
+        y = _u.autoencoder_forward(getattr(model, "propagation_{:02d}".format(step)), x,
+                                   own_convs=own_convs)
         y = y.permute(0, 2, 3, 1)[:, utop - top:utop + rows + bot]  # back to the ext rows
         prop = y.to(th.bfloat16).contiguous().view(bs, hw, 128)
     sum_r = sum_w = max_w = None
-    for sp in range(spp):
-        kernels = _c.chain_forward_nhwc(model.kernel_regressor, feats[:, sp], 128, xb=prop,
-                                        nhwc_out=False).view(bs, k * k, rows_ext, w)
-        sum_r, sum_w, max_w = model.kernel_update(
-            crop_like(rad[:, sp], kernels), kernels, sum_r, sum_w, max_w)
+    k2 = k * k
+    group_n = max(2, min(spp, int((4 << 30) // max(1, bs * k2 * hw * 4)) // 2 * 2))
+    for s0 in range(0, spp, group_n):
+        ns = min(group_n, spp - s0)
+        logits = _c.chain_samples_nhwc(model.kernel_regressor, feats, 128, prop=prop,
+                                       regress=True, sample0=s0, nsamples=ns)
+        for i in range(ns):
+            kernels = logits[:, i].view(bs, k2, rows_ext, w)
+            sum_r, sum_w, max_w = model.kernel_update(
+                crop_like(rad[:, s0 + i], kernels), kernels, sum_r, sum_w, max_w)
+        del logits
     out = sum_r / (sum_w + model.eps)                  # [bs, 3, rows_ext, w]
     y_lo, y_hi = max(y0, crop), min(y1, height - crop)
     band_out = out[..., y_lo - a:y_hi - a, crop:w - crop].contiguous()

@@ -156,7 +156,11 @@ def test_fused_adam_matches_torch(max_norm, backend):
         set_grads(mine, step, 3.0)
         set_grads(ref, step, 3.0)
         before = _lib.launch_count()
+        versions = [p._version for p in mine]
         fused.step(max_norm=max_norm)
+        # the kernels write through raw pointers; caches keyed on the autograd version
+        # counter (conv1x1.prepare, unet_fast) must still see the update
+        assert all(p._version > v for p, v in zip(mine, versions))
         if backend == "cuda":
             assert _lib.launch_count() - before == (3 if max_norm is not None else 1)
         if max_norm is not None:

@@ -79,6 +79,15 @@ def _worker(rank, world, port, shape, q):
         dd_ext, dw_ext = oracle.kernel_weighting_grad(ext, w_ext, do_ext, ds_ext)
         d_data = sharding.reduce_halo(plan, rank, dd_ext)
 
+        # the pre-allocated / side-stream variant of the same two exchanges
+        pipe = sharding.HaloPipeline(plan, rank, band.shape, "cpu")
+        pext = pipe.new_ext().fill_(float("nan"))
+        pipe.band(pext).copy_(band)
+        pipe.wait(pipe.exchange_async(pext))
+        dd2 = dd_ext.clone()
+        pipe.wait(pipe.reduce_async(dd2))
+        ok_pipe = th.equal(pext, want) and th.equal(pipe.band(dd2), d_data)
+
         out = sharding.gather_bands(plan, rank, out_ext[:, :, top:top + rows], 2)
         sum_w = sharding.gather_bands(plan, rank, sw_ext[:, top:top + rows], 1)
         d_data = sharding.gather_bands(plan, rank, d_data, 2)
@@ -87,7 +96,7 @@ def _worker(rank, world, port, shape, q):
         ro, rs = oracle.kernel_weighting(data, weights)
         rdd, rdw = oracle.kernel_weighting_grad(data, weights, d_output, d_sum_w)
         res = {
-            "ext": ok_ext,
+            "ext": ok_ext, "pipeline": ok_pipe,
             # forward / d_weights use the same per-pixel arithmetic: bit-identical
             "output": th.equal(out, ro), "sum_w": th.equal(sum_w, rs),
             "d_weights": th.equal(d_weights, rdw),

@@ -502,27 +502,36 @@ def run_secondary(a, th, dist, dev, rank, world):
                 "repo_launches_per_forward": (_lib.launch_count() - l0) / 7.0}
             del net, batch
             th.cuda.empty_cache()
-            # config 4: train step B=8, spp=8, 128x128, K=21: fwd + loss + bwd + clip + Adam
-            net = models.Multisteps(93, 3).to(dev).train()
-            iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True,
-                                                            fused_optimizer=True)
+            # config 4: train step B=8, spp=8, 128x128, K=21: fwd + loss + bwd + clip + Adam,
+            # once in strict fp32 (the reference's arithmetic) and once with cuDNN's TF32
+            # convolution paths allowed (PyTorch's default; labelled, never silent)
             batch = {"radiance": th.rand(8, 8, 3, 128, 128, device=dev),
                      "features": th.randn(8, 8, 93, 128, 128, device=dev),
                      "global_features": th.randn(8, 3, 1, 1, device=dev),
                      "target_image": th.rand(8, 3, 128, 128, device=dev)}
-
-            def train():
-                return iface.backward(batch, iface.forward(batch))
-            ms = _timed_cuda(th, train, 2, 5)
             sec["config4_train_step"] = {
-                "ms": ms, "Msamples_per_s": 8 * 8 * 128 * 128 / ms / 1e3,
                 "workload": "Multisteps(93,3) train step, B=8, spp=8, 128x128, K=21, "
                             "fwd + TonemappedRelativeMSE + bwd + clip + Adam, 1 GPU",
-                "precision": "fp32, TF32 %s (interfaces.SampleBasedDenoiserInterface policy)"
-                             % ("allowed" if iface.allow_tf32 else "off"),
-                "path": "cuDNN fp32 convs; fused splat forward / backward and fused clip+Adam "
-                        "are repo kernels"}
-            del net, iface, batch
+                "path": "cuDNN convs; fused splat forward / backward and fused clip+Adam are "
+                        "repo kernels"}
+            for label, tf32 in (("fp32_strict", False), ("tf32_convs_allowed", True)):
+                th.manual_seed(0)
+                net = models.Multisteps(93, 3).to(dev).train()
+                iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True,
+                                                                fused_optimizer=True,
+                                                                allow_tf32=tf32)
+
+                def train():
+                    return iface.backward(batch, iface.forward(batch))
+                ms = _timed_cuda(th, train, 2, 4)
+                sec["config4_train_step"][label] = {
+                    "ms": ms, "Msamples_per_s": 8 * 8 * 128 * 128 / ms / 1e3,
+                    "precision": "fp32 storage and accumulation, TF32 %s for cuDNN / cuBLAS"
+                                 % ("ALLOWED" if tf32 else "off")}
+                del net, iface
+            th.backends.cudnn.allow_tf32 = False
+            th.backends.cuda.matmul.allow_tf32 = False
+            del batch
             th.cuda.empty_cache()
     except Exception as exc:                      # the headline line must still be printed
         sec["error_config34"] = "%s: %s" % (type(exc).__name__, exc)

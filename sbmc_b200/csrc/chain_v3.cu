@@ -65,16 +65,22 @@ struct Args {
   long long *trace;                       // developer timeline (SBMC_CHAIN_TRACE builds), or null
 };
 
-// Developer timeline: CTA 0 appends (code, clock) pairs; compiled out by default.
+// Developer timeline: four threads of CTA 0 (producer, MMA issuer, lane 0 of the first
+// warp of each epilogue group) append (code, clock) pairs to their own region with
+// plain stores (no atomics: a returning atomic would sit on the critical path).
+// Compiled out by default.
 #ifdef SBMC_CHAIN_TRACE
-__device__ __forceinline__ void trace_ev(const Args &P, int code) {
-  if (P.trace && blockIdx.x == 0) {
-    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long *>(P.trace), 1ull);
-    if (i < 8000) { P.trace[2 + 2 * i] = code; P.trace[3 + 2 * i] = clock64(); }
-  }
-}
-#define TRACE(code) trace_ev(P, code)
+#define TRACE_DECL(role) int trace_n_ = 0; const int trace_role_ = (role)
+#define TRACE(code)                                                                  \
+  do {                                                                               \
+    if (P.trace && blockIdx.x == 0 && trace_n_ < 2000) {                             \
+      P.trace[(trace_role_ * 2000 + trace_n_) * 2] = (code);                         \
+      P.trace[(trace_role_ * 2000 + trace_n_) * 2 + 1] = clock64();                  \
+      ++trace_n_;                                                                    \
+    }                                                                                \
+  } while (0)
 #else
+#define TRACE_DECL(role) do { } while (0)
 #define TRACE(code) do { } while (0)
 #endif
 
@@ -212,13 +218,14 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
       if (!REGRESS)
         for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW3 + kb * kSlab, &w3map, bars + B_W, kb * 64, 0);
       uint32_t ph_fe = 0, ph_pe = 0;
+      TRACE_DECL(0);
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int n = (int)(tile / P.tiles_per_img);
         const int p0 = (int)(tile - (long long)n * P.tiles_per_img) * kTileP;
         for (int j = 0; j < npairs; ++j) {
           const bool bvalid = 2 * j + 1 < P.ns;
           mbar_wait(bars + B_F_EMPTY, ph_fe ^ 1); ph_fe ^= 1;
-          TRACE(1);                                   // F slot free, loads issued
+          TRACE(1);                                   // F slot free, issuing the loads
           mbar_expect_tx(bars + B_F_FULL, (uint32_t)((bvalid ? 4 : 2) * kSlab));
           for (int e = 0; e < (bvalid ? 2 : 1); ++e)
             for (int kb = 0; kb < 2; ++kb)
@@ -261,6 +268,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
       uint32_t ph_oe = 0;                        // bit 3 e + ob
       uint32_t has_prev = 0;                     // bit e
       int ring = 0;
+      TRACE_DECL(1);
       auto wait_ar = [&](int e) {
         mbar_wait(bars + B_AR0 + e, (ph_ar >> e) & 1);
         ph_ar ^= 1u << e;
@@ -366,11 +374,16 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
     const uint32_t x = lane_base + e * 192, y = x + 128;
     float *sb1 = sB1 + e * kHid;
     uint32_t ph_acc = 0, ph_m = 0, ph_of = 0;       // ph_of: bit ob
+    TRACE_DECL(2 + e);
     long long cur_n = -1;
     for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const long long n = tile / P.tiles_per_img;
       const long long p = (tile - n * P.tiles_per_img) * kTileP + row;
+#ifdef SBMC_CHAIN_NOSTORE                            // developer experiment: no output stores
+      const bool valid = p < 0;
+#else
       const bool valid = p < P.hw;
+#endif
       for (int j = 0; j < npairs; ++j) {
         const int sl = 2 * j + e;                    // sample index within this launch
         if (sl >= P.ns) continue;

@@ -15,7 +15,7 @@ NAMES = {1: "prod: F slot free, loads issued", 10: "mma: waiting for F", 11: "mm
          34: "eg b: L3 acc ready", 35: "eg b: E3 done"}
 dev = th.device("cuda", 0)
 lib = _lib.load()
-trace = th.zeros(2 + 2 * 8000, dtype=th.int64, device=dev)
+trace = th.zeros(4 * 2000 * 2, dtype=th.int64, device=dev)
 ctypes.c_void_p.in_dll(lib, "sbmc_b200_debug_pointer").value = trace.data_ptr()
 h, w, spp = 720, 1280, 4
 emb = modules.ConvChain(256, 128, width=128, depth=3, ksize=1, pad=False).to(dev).eval()
@@ -28,9 +28,8 @@ with th.no_grad():
     trace.zero_()
     conv1x1.chain_samples_nhwc(emb, feats, 128, prop=prop, want_mean=True)
     th.cuda.synchronize()
-t = trace.cpu().tolist()
-n = min(t[0], 8000)
-ev = sorted((t[3 + 2 * i], t[2 + 2 * i]) for i in range(n))
+t = trace.cpu().view(4, 2000, 2).tolist()
+ev = sorted((c, code) for role in t for code, c in role if c)
 t0 = ev[0][0]
 # print items 10..13 (steady state)
 start = [i for i, (c, code) in enumerate(ev) if code == 10]

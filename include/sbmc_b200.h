@@ -224,6 +224,12 @@ SBMC_API int sbmc_upsample_concat_nhwc_bf16(const void *low, const void *skip, v
                                    int64_t n, int hl, int wl, int h, int w, int cu,
                                    int cs, void *stream);
 
+/* 2 x 2 / stride 2 max pooling (the U-net's `downsample`, sbmc/modules.py:296-299:
+ * nn.MaxPool2d(2, 2), floor mode) on bf16 channels-innermost x [n][h][w][c] ->
+ * y [n][h/2][w/2][c]; c multiple of 8, 16-byte aligned pointers. */
+SBMC_API int sbmc_maxpool2x2_nhwc_bf16(const void *x, void *y, int64_t n, int h, int w, int c,
+                                       void *stream);
+
 /* y = act(y + bias[channel]) in place on bf16 channels-innermost y [pixels][c]
  * (the bias + activation after every U-net convolution, modules.py:176-181);
  * act: 0 none, 1 ReLU, 2 LeakyReLU(0.01); c multiple of 8. */

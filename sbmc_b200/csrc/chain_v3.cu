@@ -51,6 +51,11 @@ constexpr int kCtrlWarps = 4;
 constexpr int kEgWarps = 8;               // epilogue warps per stream
 constexpr int kThreads = 32 * (kCtrlWarps + 2 * kEgWarps);
 constexpr int kChunk = 64;                // output channels per last-layer chunk (regressor)
+#ifdef SBMC_CHAIN_NOSTORE                 // developer experiment: no output stores
+constexpr bool kStoreOn = false;
+#else
+constexpr bool kStoreOn = true;
+#endif
 
 struct Args {
   const float *b1; long long b1_img;      // first-layer bias, optionally per image
@@ -379,11 +384,7 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
     for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const long long n = tile / P.tiles_per_img;
       const long long p = (tile - n * P.tiles_per_img) * kTileP + row;
-#ifdef SBMC_CHAIN_NOSTORE                            // developer experiment: no output stores
-      const bool valid = p < 0;
-#else
-      const bool valid = p < P.hw;
-#endif
+      const bool valid = kStoreOn && p < P.hw;
       for (int j = 0; j < npairs; ++j) {
         const int sl = 2 * j + e;                    // sample index within this launch
         if (sl >= P.ns) continue;
@@ -411,26 +412,30 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
           mbar_wait(bars + B_ACC0 + e, ph_acc); ph_acc ^= 1;
           if (wi == 0 && lane == 0) TRACE(24 + 10 * e);
           tcgen05_fence_after();
-          __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(P.out) + n * P.out_img +
-                               (long long)(P.s0 + sl) * P.out_smp + p * kHid + half * 64;
+          // this thread's 64 channels -> 32 packed words -> quad transpose -> 4 x 256-bit
+          // stores, each completing 8 lines (see umma.cuh::quad_transpose32)
+          {
+            uint32_t q[32];
 #pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int c0 = half * 64 + it * 32;
-            float v[32];
-            tmem_ld_32x32b_x32(x + c0, v);
-            if (valid) {
+            for (int it = 0; it < 2; ++it) {
+              const int c0 = half * 64 + it * 32;
+              float v[32];
+              tmem_ld_32x32b_x32(x + c0, v);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 ba = *reinterpret_cast<const float4 *>(sB3 + c0 + 8 * g);
-                const float4 bb = *reinterpret_cast<const float4 *>(sB3 + c0 + 8 * g + 4);
-                uint4 q;
-                q.x = pack_bf16(v[8 * g + 0] + ba.x, v[8 * g + 1] + ba.y);
-                q.y = pack_bf16(v[8 * g + 2] + ba.z, v[8 * g + 3] + ba.w);
-                q.z = pack_bf16(v[8 * g + 4] + bb.x, v[8 * g + 5] + bb.y);
-                q.w = pack_bf16(v[8 * g + 6] + bb.z, v[8 * g + 7] + bb.w);
-                stg128(dst + it * 32 + 8 * g, q);
+              for (int g = 0; g < 8; ++g) {
+                const float4 b = *reinterpret_cast<const float4 *>(sB3 + c0 + 4 * g);
+                q[16 * it + 2 * g] = pack_bf16(v[4 * g] + b.x, v[4 * g + 1] + b.y);
+                q[16 * it + 2 * g + 1] = pack_bf16(v[4 * g + 2] + b.z, v[4 * g + 3] + b.w);
               }
             }
+            quad_transpose32(q, lane);
+            const long long prow = p - (lane & 3);             // first pixel of the quad
+            __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(P.out) + n * P.out_img +
+                                 (long long)(P.s0 + sl) * P.out_smp + prow * kHid + half * 64 +
+                                 (lane & 3) * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (kStoreOn && prow + k < P.hw) stg256(dst + k * kHid, q + 8 * k);
           }
           tcgen05_fence_before();
           __syncwarp();
@@ -440,15 +445,16 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
           if (do_mean && sl == P.ns - 1) {
             mbar_wait(bars + B_M_FULL, ph_m); ph_m ^= 1;
             tcgen05_fence_after();
+            uint32_t mq[32];
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
               const int c0 = half * 64 + it * 32;
               float v[32];
               tmem_ld_32x32b_x32(lane_base + 384 + c0, v);
-              if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], P.inv_spp, sB3[c0 + i]);
-                if (P.mean_f32) {
+              for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], P.inv_spp, sB3[c0 + i]);
+              {
+                if (P.mean_f32 && valid) {
                   float *m = reinterpret_cast<float *>(P.mean) + n * P.mean_img + p * kHid + c0;
 #pragma unroll
                   for (int g = 0; g < 8; ++g) {
@@ -457,20 +463,21 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
                     q.z = __float_as_uint(v[4 * g + 2]); q.w = __float_as_uint(v[4 * g + 3]);
                     stg128(m + 4 * g, q);
                   }
-                } else {
-                  __nv_bfloat16 *m = reinterpret_cast<__nv_bfloat16 *>(P.mean) + n * P.mean_img +
-                                     p * kHid + c0;
-#pragma unroll
-                  for (int g = 0; g < 4; ++g) {
-                    uint4 q;
-                    q.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]);
-                    q.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-                    q.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]);
-                    q.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-                    stg128(m + 8 * g, q);
-                  }
                 }
               }
+              if (!P.mean_f32) {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) mq[16 * it + g] = pack_bf16(v[2 * g], v[2 * g + 1]);
+              }
+            }
+            if (!P.mean_f32) {
+              quad_transpose32(mq, lane);
+              const long long prow = p - (lane & 3);
+              __nv_bfloat16 *m = reinterpret_cast<__nv_bfloat16 *>(P.mean) + n * P.mean_img +
+                                 prow * kHid + half * 64 + (lane & 3) * 16;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (kStoreOn && prow + k < P.hw) stg256(m + k * kHid, mq + 8 * k);
             }
             tcgen05_fence_before();
             __syncwarp();

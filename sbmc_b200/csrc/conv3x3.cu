@@ -199,33 +199,55 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
       const int buf = (NT == 128) ? (it & 1) : 0;
       mbar_wait(bars + B_ACCF + buf, (ph >> buf) & 1); ph ^= 1u << buf;
       tcgen05_fence_after();
-      const int y = t.y0 + g, x = t.x0 + px;
-      const bool valid = y < P.H && x < P.W;
-      __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + x) * P.Cout + t.n0;
+      // 64 channels per step: 2 x tcgen05.ld -> bias, activation -> 32 packed words ->
+      // transpose inside the lane quad -> 4 x 256-bit stores that each complete 8 lines
+      // (umma.cuh::quad_transpose32; one 16-byte store per lane would touch 32 lines)
+      const int y = t.y0 + g;
+      const int xq = t.x0 + px - (lane & 3);            // first pixel of this lane's quad
+      __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + xq) * P.Cout + t.n0 +
+                           (lane & 3) * 16;
       const float *bias = P.bias + t.n0;
 #pragma unroll 1
-      for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 32) {
+      for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 64) {
         const uint32_t col = (NT == 128) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
-        float v[32];
-        tmem_ld_32x32b_x32(lane_base + col, v);
-        if (valid) {
+        uint32_t q[32];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * q4));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * q4 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float r[8];
+        for (int hh = 0; hh < 2; ++hh) {
+          float v[32];
+          tmem_ld_32x32b_x32(lane_base + col + 32 * hh, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float u = v[8 * q4 + i] + bb[i];
-              if (P.act == 1) u = fmaxf(u, 0.f);
-              else if (P.act == 2) u = fmaxf(u, 0.01f * u);
-              r[i] = u;
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 32 * hh + 4 * q4));
+            float u0 = v[4 * q4] + b.x, u1 = v[4 * q4 + 1] + b.y;
+            float u2 = v[4 * q4 + 2] + b.z, u3 = v[4 * q4 + 3] + b.w;
+            if (P.act == 1) {
+              u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); u2 = fmaxf(u2, 0.f); u3 = fmaxf(u3, 0.f);
+            } else if (P.act == 2) {
+              u0 = fmaxf(u0, 0.01f * u0); u1 = fmaxf(u1, 0.01f * u1);
+              u2 = fmaxf(u2, 0.01f * u2); u3 = fmaxf(u3, 0.01f * u3);
             }
-            uint4 q;
-            q.x = pack_bf16(r[0], r[1]); q.y = pack_bf16(r[2], r[3]);
-            q.z = pack_bf16(r[4], r[5]); q.w = pack_bf16(r[6], r[7]);
-            stg128(dst + c0 + 8 * q4, q);
+            q[16 * hh + 2 * q4] = pack_bf16(u0, u1);
+            q[16 * hh + 2 * q4 + 1] = pack_bf16(u2, u3);
+          }
+        }
+        if (NT == 256) {
+          // the epilogue runs after the tile's last MMA: the shuffles have the shared-memory
+          // crossbar to themselves
+          quad_transpose32(q, lane);
+          if (y < P.H) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (xq + k < P.W) stg256(dst + (long long)k * P.Cout + c0, q + 8 * k);
+          }
+        } else {
+          // NT = 128: this epilogue overlaps the next tile's MMAs, whose operand reads
+          // already saturate the shared-memory data path that shuffles share (measured:
+          // the transposed variant made the 128 -> 128 layer 30 % slower,
+          // profiles/r2f_convs.jsonl): plain 256-bit stores of the thread's own row
+          if (y < P.H && xq + (lane & 3) < P.W) {
+            __nv_bfloat16 *own = dst - (lane & 3) * 16 + (long long)(lane & 3) * P.Cout + c0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stg256(own + 16 * k, q + 8 * k);
           }
         }
       }

@@ -126,5 +126,41 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
+// ---- epilogue stores: 4 x 4 transpose of 32-byte elements inside a lane quad ----
+// A TMEM epilogue thread owns one tensor row (pixel): its 128 output bytes are
+// contiguous, but one warp-wide store then touches 32 different 128-byte lines and
+// the LSU retires ~1 line per cycle -- measured: the 16-byte-per-lane stores of the
+// embedding chain cost as much as the rest of the kernel (profiles/r2e_*).  Two
+// butterfly exchanges (shfl.xor 2, then 1) turn "lane q holds the four 32-byte
+// elements of row q" into "lane q holds element q of the four rows of its quad",
+// so that a 256-bit store instruction writes 8 complete 128-byte lines.
+// In: r[8 c + i] = word i of element c of this lane's row.  Out: r[8 k + i] = word i
+// of element (lane & 3) of the row of lane (lane & ~3) + k.
+__device__ __forceinline__ void quad_transpose32(uint32_t (&r)[32], int lane) {
+  const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t lo = r[i], hi = r[i + 16];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, b1 ? lo : hi, 2);
+    r[i] = b1 ? recv : lo;
+    r[i + 16] = b1 ? hi : recv;
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t x = r[16 * rr + i], y = r[16 * rr + 8 + i];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, b0 ? x : y, 1);
+      r[16 * rr + i] = b0 ? recv : x;
+      r[16 * rr + 8 + i] = b0 ? y : recv;
+    }
+}
+// 256-bit global store (sm_100: STG.256), p 32-byte aligned.
+__device__ __forceinline__ void stg256(void *p, const uint32_t *v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 #endif  // __CUDACC__
 }  // namespace sbmc

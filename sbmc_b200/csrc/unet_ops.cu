@@ -25,37 +25,43 @@ __device__ __forceinline__ void unpack8(const uint4 &q, float (&f)[8]) {
   }
 }
 
+// One block row (blockIdx.y) per output image row: all index arithmetic is 32-bit
+// with one division per 16-byte chunk (the first version decomposed a 64-bit flat
+// index with five 64-bit divisions per chunk and was instruction-bound).
 __global__ void __launch_bounds__(256)
 upsample_concat_kernel(const uint4 *__restrict__ low, const uint4 *__restrict__ skip,
-                       uint4 *__restrict__ out, i64 n, int hl, int wl, int h, int w, int cu8,
+                       uint4 *__restrict__ out, int hl, int wl, int h, int w, int cu8,
                        int cs8, float sy_scale, float sx_scale) {
   const int ct8 = cu8 + cs8;
-  const i64 total = n * h * w * ct8;
-  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (i64)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % ct8);
-    const i64 pix = idx / ct8;
+  const int y = blockIdx.x % h;
+  const i64 img = blockIdx.x / h;
+  float sy = sy_scale * (y + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  const int y0 = (int)sy;
+  const int y1 = y0 + (y0 < hl - 1 ? 1 : 0);
+  const float ly = sy - y0, hy = 1.f - ly;
+  const uint4 *row0 = low + (img * hl + y0) * (i64)wl * cu8;
+  const uint4 *row1 = low + (img * hl + y1) * (i64)wl * cu8;
+  const uint4 *srow = skip + (img * h + y) * (i64)w * cs8;
+  uint4 *orow = out + (img * h + y) * (i64)w * ct8;
+  const int total = w * ct8;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+    const int x = idx / ct8;
+    const int c8 = idx - x * ct8;
     if (c8 >= cu8) {  // skip connection: straight copy
-      out[idx] = __ldg(skip + pix * cs8 + (c8 - cu8));
+      orow[idx] = __ldg(srow + x * cs8 + (c8 - cu8));
       continue;
     }
-    const int x = (int)(pix % w);
-    const int y = (int)((pix / w) % h);
-    const i64 img = pix / ((i64)w * h);
-    float sy = sy_scale * (y + 0.5f) - 0.5f;
     float sx = sx_scale * (x + 0.5f) - 0.5f;
-    sy = sy < 0.f ? 0.f : sy;
     sx = sx < 0.f ? 0.f : sx;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < hl - 1 ? 1 : 0), x1 = x0 + (x0 < wl - 1 ? 1 : 0);
-    const float ly = sy - y0, lx = sx - x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const uint4 *base = low + img * hl * wl * cu8 + c8;
+    const int x0 = (int)sx;
+    const int x1 = x0 + (x0 < wl - 1 ? 1 : 0);
+    const float lx = sx - x0, hx = 1.f - lx;
     float a[8], b[8], c[8], d[8];
-    unpack8(__ldg(base + ((i64)y0 * wl + x0) * cu8), a);
-    unpack8(__ldg(base + ((i64)y0 * wl + x1) * cu8), b);
-    unpack8(__ldg(base + ((i64)y1 * wl + x0) * cu8), c);
-    unpack8(__ldg(base + ((i64)y1 * wl + x1) * cu8), d);
+    unpack8(__ldg(row0 + x0 * cu8 + c8), a);
+    unpack8(__ldg(row0 + x1 * cu8 + c8), b);
+    unpack8(__ldg(row1 + x0 * cu8 + c8), c);
+    unpack8(__ldg(row1 + x1 * cu8 + c8), d);
     uint4 q;
     __nv_bfloat162 *o = reinterpret_cast<__nv_bfloat162 *>(&q);
 #pragma unroll
@@ -65,7 +71,36 @@ upsample_concat_kernel(const uint4 *__restrict__ low, const uint4 *__restrict__ 
                        ly * (hx * c[2 * i + 1] + lx * d[2 * i + 1]);
       o[i] = __floats2bfloat162_rn(v0, v1);
     }
-    out[idx] = q;
+    orow[idx] = q;
+  }
+}
+
+// 2 x 2 max pooling, stride 2 (the U-net's `downsample`, sbmc/modules.py:296-299:
+// nn.MaxPool2d(2, 2), floor mode) on bf16 channels-innermost tensors: one thread per
+// 16-byte chunk (8 channels) of an output pixel.
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, int h, int w, int c8) {
+  const int ho = h / 2, wo = w / 2;
+  const int yo = blockIdx.x % ho;
+  const i64 img = blockIdx.x / ho;
+  const uint4 *r0 = x + (img * h + 2 * yo) * (i64)w * c8;
+  const uint4 *r1 = r0 + (i64)w * c8;
+  uint4 *orow = y + (img * ho + yo) * (i64)wo * c8;
+  const int total = wo * c8;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+    const int xo = idx / c8;
+    const int c = idx - xo * c8;
+    const uint4 a = __ldg(r0 + (2 * xo) * c8 + c), b = __ldg(r0 + (2 * xo + 1) * c8 + c);
+    const uint4 e = __ldg(r1 + (2 * xo) * c8 + c), f = __ldg(r1 + (2 * xo + 1) * c8 + c);
+    uint4 q;
+    const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a);
+    const __nv_bfloat162 *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+    const __nv_bfloat162 *pe = reinterpret_cast<const __nv_bfloat162 *>(&e);
+    const __nv_bfloat162 *pf = reinterpret_cast<const __nv_bfloat162 *>(&f);
+    __nv_bfloat162 *o = reinterpret_cast<__nv_bfloat162 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __hmax2(__hmax2(pa[i], pb[i]), __hmax2(pe[i], pf[i]));
+    orow[idx] = q;
   }
 }
 
@@ -94,16 +129,20 @@ extern "C" int sbmc_upsample_concat_nhwc_bf16(const void *low, const void *skip,
     set_error("upsample_concat: channel counts must be multiples of 8 (got %d, %d)", cu, cs);
     return SBMC_EUNSUPPORTED;
   }
-  const i64 total = n * h * w * ((cu + cs) / 8);
-  i64 blocks = ceil_div(total, 256);
-  const i64 cap = (i64)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
+  if (n * h >= (1ll << 31) || (i64)w * ((cu + cs) / 8) >= (1ll << 31)) {
+    set_error("upsample_concat: image too large");
+    return SBMC_EUNSUPPORTED;
+  }
+  const int per_row = w * ((cu + cs) / 8);
+  int bx = (per_row + 255) / 256;
+  if (bx > 8) bx = 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_OTHER, st);
-    upsample_concat_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+    const dim3 grid((unsigned)(n * h), (unsigned)bx);     // x: image rows, y: chunks of a row
+    upsample_concat_kernel<<<grid, 256, 0, st>>>(
         static_cast<const uint4 *>(low), static_cast<const uint4 *>(skip),
-        static_cast<uint4 *>(out), n, hl, wl, h, w, cu / 8, cs / 8, (float)hl / (float)h,
+        static_cast<uint4 *>(out), hl, wl, h, w, cu / 8, cs / 8, (float)hl / (float)h,
         (float)wl / (float)w);
   }
   count_launch();
@@ -193,30 +232,48 @@ extern "C" int sbmc_bias_act_nhwc_bf16(void *y, const float *bias, int64_t pixel
 // ---------------------------------------------------------------------------
 namespace sbmc {
 
-__global__ void __launch_bounds__(128)
+// Block = 64 pixels x all channels through shared memory: per channel pair a warp
+// reads 2 x 32 consecutive floats of two planes (coalesced) and writes one packed
+// bf16x2 word per pixel into a padded [64][cpad / 2 + 1] tile (conflict-free); the
+// tile is then stored as 64 x cpad x 2 contiguous bytes, 16 bytes per lane.
+constexpr int kT2Px = 64;
+__global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64 n, int c,
                          i64 hw, i64 x_img, i64 y_img8, int cpad8) {
-  const i64 tiles = (hw + 127) / 128;
+  extern __shared__ uint32_t tile[];               // [kT2Px][cpad / 2 + 1]
+  const int cw = cpad8 * 4;                        // bf16x2 words per pixel
+  const int pitch = cw + 1;
+  const i64 tiles = (hw + kT2Px - 1) / kT2Px;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (i64 t = blockIdx.x; t < n * tiles; t += gridDim.x) {
     const i64 img = t / tiles;
-    const i64 p = (t - img * tiles) * 128 + threadIdx.x;
-    if (p >= hw) continue;
-    const float *src = x + img * x_img + p;
-    uint4 *dst = y + img * y_img8 + p * cpad8;
-#pragma unroll 2
-    for (int c8 = 0; c8 < cpad8; ++c8) {
-      float v[8];
+    const i64 p0 = (t - img * tiles) * kT2Px;
+    const float *src = x + img * x_img + p0;
+    for (int cp = warp; cp < cw; cp += 8) {        // channel pair (2 cp, 2 cp + 1)
+      const int c0 = 2 * cp;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int ch = c8 * 8 + j;
-        v[j] = ch < c ? __ldg(src + (i64)ch * hw) : 0.f;
+      for (int h2 = 0; h2 < kT2Px / 32; ++h2) {
+        const int px = h2 * 32 + lane;
+        float a = 0.f, b = 0.f;
+        if (p0 + px < hw) {
+          if (c0 < c) a = __ldg(src + (i64)c0 * hw + px);
+          if (c0 + 1 < c) b = __ldg(src + (i64)(c0 + 1) * hw + px);
+        }
+        const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        tile[px * pitch + cp] = *reinterpret_cast<const uint32_t *>(&v);
       }
-      uint4 q;
-      __nv_bfloat162 *o = reinterpret_cast<__nv_bfloat162 *>(&q);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      dst[c8] = q;
     }
+    __syncthreads();
+    uint4 *dst = y + img * y_img8 + p0 * cpad8;
+    const int nchunks = kT2Px * cpad8;
+    for (int i = threadIdx.x; i < nchunks; i += 256) {
+      const int px = i / cpad8, c8 = i - px * cpad8;
+      if (p0 + px < hw) {
+        const uint32_t *r = tile + px * pitch + c8 * 4;
+        dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -235,13 +292,52 @@ extern "C" int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void
     set_error("nchw_to_nhwc: null or misaligned pointer");
     return SBMC_EINVAL;
   }
-  const i64 tiles = n * ((hw + 127) / 128);
-  i64 blocks = tiles < (i64)num_sms() * 16 ? tiles : (i64)num_sms() * 16;
+  const i64 tiles = n * ((hw + kT2Px - 1) / kT2Px);
+  i64 blocks = tiles < (i64)num_sms() * 8 ? tiles : (i64)num_sms() * 8;
+  const size_t smem = (size_t)kT2Px * (cpad / 2 + 1) * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    set_error("nchw_to_nhwc: cpad %d too large", cpad);
+    return SBMC_EUNSUPPORTED;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_OTHER, st);
-    nchw_to_nhwc_bf16_kernel<<<(unsigned)blocks, 128, 0, st>>>(
+    nchw_to_nhwc_bf16_kernel<<<(unsigned)blocks, 256, smem, st>>>(
         x, static_cast<uint4 *>(y), n, c, hw, x_img_stride, y_img_stride / 8, cpad / 8);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  note_path(1);
+  return SBMC_OK;
+}
+
+// 2 x 2 / stride 2 max pooling on bf16 channels-innermost x [n][h][w][c] ->
+// y [n][h/2][w/2][c] (floor mode, like nn.MaxPool2d(2, 2)); c multiple of 8.
+extern "C" int sbmc_maxpool2x2_nhwc_bf16(const void *x, void *y, int64_t n, int h, int w, int c,
+                                         void *stream) {
+  using namespace sbmc;
+  if (n < 0 || h < 2 || w < 2 || c < 8 || c % 8) {
+    set_error("maxpool2x2: invalid shape (c must be a multiple of 8, h, w >= 2)");
+    return SBMC_EINVAL;
+  }
+  if (n == 0) return SBMC_OK;
+  if (!x || !y || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15)) {
+    set_error("maxpool2x2: null or misaligned pointer");
+    return SBMC_EINVAL;
+  }
+  const int ho = h / 2, wo = w / 2;
+  if (n * ho >= (1ll << 31) || (i64)w * (c / 8) >= (1ll << 31)) {
+    set_error("maxpool2x2: image too large");
+    return SBMC_EUNSUPPORTED;
+  }
+  int bx = (wo * (c / 8) + 255) / 256;
+  if (bx > 8) bx = 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    KernelTimer timer(SBMC_KERNEL_OTHER, st);
+    const dim3 grid((unsigned)(n * ho), (unsigned)bx);
+    maxpool2x2_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4 *>(x),
+                                            static_cast<uint4 *>(y), h, w, c / 8);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());

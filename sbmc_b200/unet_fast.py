@@ -126,12 +126,40 @@ def _chain(chain, x, own_convs=True):
     return x
 
 
+def _maxpool2x2(x):
+    """nn.MaxPool2d(2, 2) on an NCHW-shaped bf16 channels_last tensor (own kernel)."""
+    n, c, h, w = x.shape
+    if not x.is_contiguous(memory_format=th.channels_last):
+        x = x.contiguous(memory_format=th.channels_last)
+    y = th.empty((n, c, h // 2, w // 2), device=x.device, dtype=th.bfloat16,
+                 memory_format=th.channels_last)
+    lib = _lib.load()
+    with th.cuda.device(x.device):
+        rc = lib.sbmc_maxpool2x2_nhwc_bf16(x.data_ptr(), y.data_ptr(), n, h, w, c,
+                                           th.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "maxpool2x2")
+    return y
+
+
+def _is_pool2x2(m):
+    def pair(v):
+        return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    return (isinstance(m, th.nn.MaxPool2d) and pair(m.kernel_size) == (2, 2)
+            and pair(m.stride) == (2, 2) and pair(m.padding) == (0, 0)
+            and pair(m.dilation) == (1, 1) and not m.ceil_mode)
+
+
 def _level(level, x, own_convs):
     from .modules import _upsample_concat
     left = _chain(level.left, x, own_convs)
     if level.is_last:
         return left
-    coarse = _level(level.next_level, level.downsample(left), own_convs)
+    if own_convs and _is_pool2x2(level.downsample) and left.shape[1] % 8 == 0 \
+            and left.shape[2] >= 2 and left.shape[3] >= 2:
+        pooled = _maxpool2x2(left)
+    else:
+        pooled = level.downsample(left)
+    coarse = _level(level.next_level, pooled, own_convs)
     return _chain(level.right, _upsample_concat(coarse, left), own_convs)
 
 

@@ -65,3 +65,36 @@ def test_unet_fast_path_with_own_convs_matches_fp32_module():
     e_own = ((got - ref).norm() / ref.norm()).item()
     e_lib = ((lib - ref).norm() / ref.norm()).item()
     assert e_own < 3e-2 and e_own < 1.5 * e_lib + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 128, 40, 72), (1, 256, 7, 9), (3, 8, 2, 2)])
+def test_maxpool2x2_matches_torch(shape):
+    th.manual_seed(1)
+    x = th.randn(*shape, device="cuda").to(th.bfloat16).contiguous(memory_format=th.channels_last)
+    got = unet_fast._maxpool2x2(x)
+    want = F.max_pool2d(x, 2, 2)
+    assert got.shape == want.shape and th.equal(got, want)
+
+
+@pytest.mark.gpu
+def test_upsample_concat_and_layout_change_kernels_after_their_rewrite():
+    """Both kernels were re-indexed / re-tiled in round 2: same results as torch."""
+    from sbmc_b200 import conv1x1
+    th.manual_seed(2)
+    for (n, cu, hl, wl, cs, h, w) in [(1, 256, 20, 36, 128, 40, 72), (2, 16, 3, 5, 8, 7, 11)]:
+        low = th.randn(n, cu, hl, wl, device="cuda").to(th.bfloat16).contiguous(memory_format=th.channels_last)
+        skip = th.randn(n, cs, h, w, device="cuda").to(th.bfloat16).contiguous(memory_format=th.channels_last)
+        got = modules._upsample_concat(low, skip)
+        up = F.interpolate(low.float(), size=(h, w), mode="bilinear", align_corners=False)
+        want = th.cat([up, skip.float()], 1)
+        assert got.shape == want.shape
+        assert (got.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+        assert th.equal(got[:, cu:], skip)
+    for shape in [(2, 3, 93, 9, 13), (1, 1, 128, 16, 32), (3, 5, 7, 11), (1, 93, 64, 128)]:
+        x = th.randn(*shape, device="cuda")
+        got = conv1x1.to_nhwc_bf16(x)
+        c, h, w = shape[-3:]
+        want = th.zeros(shape[:-3] + (h * w, 128), device="cuda", dtype=th.bfloat16)
+        want[..., :c] = x.reshape(shape[:-3] + (c, h * w)).transpose(-1, -2)
+        assert th.equal(got, want)

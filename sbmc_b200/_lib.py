@@ -86,9 +86,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    # (re)build when the library is absent OR older than csrc/ / include/ (a stale .so
+    # loaded against the current ctypes SIGNATURES could corrupt memory silently);
+    # build() is a no-op when nothing changed.  Without nvcc an existing library is
+    # used as it is -- the GPU box runs the prebuilt file.
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
-        from . import build as _build
         _build.build()
+    elif _build.nvcc_available():
+        try:
+            _build.build()
+        except RuntimeError as e:
+            raise SbmcB200Error("libsbmc_b200.so is older than its sources and the rebuild "
+                                "failed: %s" % e)
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:

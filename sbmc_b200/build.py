@@ -3,6 +3,8 @@
 No torch involvement: the library is plain CUDA behind ``extern "C"`` entry
 points (include/sbmc_b200.h).  nvcc cross-compiles without a GPU.
 """
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -34,24 +36,58 @@ def _nvcc():
     return cand
 
 
+def nvcc_available():
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return os.path.exists(cand)
+
+
 def _sources():
     return [os.path.join(CSRC, s) for s in SOURCES
             if os.path.exists(os.path.join(CSRC, s))]
 
 
+HASH_PATH = os.path.join(HERE, "build", "source.sha1")
+
+
+def _source_hash():
+    """Content hash of everything the library is built from (sources, headers, flags):
+    unlike mtimes it survives the copy onto the GPU box."""
+    h = hashlib.sha1()
+    paths = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    paths += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
+    for path in paths:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fid:
+            h.update(fid.read())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags() + SOURCES).encode())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(HASH_PATH) as fid:
+        return fid.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library; returns its path."""
+    """Compile every CUDA source into one shared library; returns its path.
+    Processes that race here (one rank per GPU) serialise on a file lock and all but
+    the first find the library up to date."""
     if not force and not _stale():
         return LIB_PATH
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -80,6 +116,8 @@ def build(force=False, verbose=False):
         "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
         "-Xlinker", "--exclude-libs,ALL"]
     subprocess.check_call(cmd)
+    with open(HASH_PATH, "w") as fid:
+        fid.write(_source_hash())
     return LIB_PATH
 
 

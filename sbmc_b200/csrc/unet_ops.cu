@@ -236,7 +236,7 @@ namespace sbmc {
 // reads 2 x 32 consecutive floats of two planes (coalesced) and writes one packed
 // bf16x2 word per pixel into a padded [64][cpad / 2 + 1] tile (conflict-free); the
 // tile is then stored as 64 x cpad x 2 contiguous bytes, 16 bytes per lane.
-constexpr int kT2Px = 64;
+constexpr int kT2Px = 128;
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64 n, int c,
                          i64 hw, i64 x_img, i64 y_img8, int cpad8) {
@@ -245,30 +245,42 @@ nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64
   const int pitch = cw + 1;
   const i64 tiles = (hw + kT2Px - 1) / kT2Px;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cw_real = (c + 1) / 2;                 // channel pairs that hold data
   for (i64 t = blockIdx.x; t < n * tiles; t += gridDim.x) {
     const i64 img = t / tiles;
     const i64 p0 = (t - img * tiles) * kT2Px;
     const float *src = x + img * x_img + p0;
-    for (int cp = warp; cp < cw; cp += 8) {        // channel pair (2 cp, 2 cp + 1)
-      const int c0 = 2 * cp;
+    const bool full = p0 + kT2Px <= hw;
+    // two channel pairs per iteration: 16 independent 128-byte row reads in flight per warp
+    for (int cp = 2 * warp; cp < cw; cp += 16) {
+      float a[2][4], b[2][4];
 #pragma unroll
-      for (int h2 = 0; h2 < kT2Px / 32; ++h2) {
-        const int px = h2 * 32 + lane;
-        float a = 0.f, b = 0.f;
-        if (p0 + px < hw) {
-          if (c0 < c) a = __ldg(src + (i64)c0 * hw + px);
-          if (c0 + 1 < c) b = __ldg(src + (i64)(c0 + 1) * hw + px);
+      for (int u = 0; u < 2; ++u) {
+        const int c0 = 2 * (cp + u);
+#pragma unroll
+        for (int h4 = 0; h4 < 4; ++h4) {
+          const int px = h4 * 32 + lane;
+          const bool ok = (cp + u) < cw_real && (full || p0 + px < hw);
+          a[u][h4] = (ok && c0 < c) ? __ldg(src + (i64)c0 * hw + px) : 0.f;
+          b[u][h4] = (ok && c0 + 1 < c) ? __ldg(src + (i64)(c0 + 1) * hw + px) : 0.f;
         }
-        const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-        tile[px * pitch + cp] = *reinterpret_cast<const uint32_t *>(&v);
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int h4 = 0; h4 < 4; ++h4) {
+          if (cp + u < cw) {
+            const __nv_bfloat162 v = __floats2bfloat162_rn(a[u][h4], b[u][h4]);
+            tile[(h4 * 32 + lane) * pitch + cp + u] = *reinterpret_cast<const uint32_t *>(&v);
+          }
+        }
     }
     __syncthreads();
     uint4 *dst = y + img * y_img8 + p0 * cpad8;
     const int nchunks = kT2Px * cpad8;
     for (int i = threadIdx.x; i < nchunks; i += 256) {
       const int px = i / cpad8, c8 = i - px * cpad8;
-      if (p0 + px < hw) {
+      if (full || p0 + px < hw) {
         const uint32_t *r = tile + px * pitch + c8 * 4;
         dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
       }
@@ -295,10 +307,12 @@ extern "C" int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void
   const i64 tiles = n * ((hw + kT2Px - 1) / kT2Px);
   i64 blocks = tiles < (i64)num_sms() * 8 ? tiles : (i64)num_sms() * 8;
   const size_t smem = (size_t)kT2Px * (cpad / 2 + 1) * sizeof(uint32_t);
-  if (smem > 48 * 1024) {
+  if (smem > 96 * 1024) {
     set_error("nchw_to_nhwc: cpad %d too large", cpad);
     return SBMC_EUNSUPPORTED;
   }
+  SBMC_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_bf16_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_OTHER, st);

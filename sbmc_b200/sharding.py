@@ -381,6 +381,12 @@ def multisteps_forward_sharded(model, samples, rank, world, overlap=144, group=N
     crop = (model.ksize - 1) // 2
     if overlap % 4 or overlap < crop:
         raise ValueError("overlap must be a multiple of 4 and >= (K-1)/2")
+    if height % 4:
+        # the U-net pools twice: with H % 4 != 0 MaxPool2d floors and the bilinear
+        # upsampling rescales by the BAND's height, so band rows would differ from the
+        # unsharded forward (pad the image to a multiple of 4 first)
+        raise ValueError("tiled inference needs an image height that is a multiple of 4, "
+                         "got %d" % height)
     plan = BandPlan(height, world, model.ksize, align=4)
     a, b, top = model_band_rows(plan, rank, overlap)
     dev = th.device("cuda", th.cuda.current_device()) if th.cuda.is_available() \
@@ -446,6 +452,9 @@ def multisteps_forward_halo(model, samples, rank, world, unet_pad=64, group=None
     crop = (k - 1) // 2
     if unet_pad % 4 or not model._nhwc_pipeline_ok(nf):
         raise ValueError("halo mode needs unet_pad % 4 == 0 and the 128-wide 1x1 chains")
+    if height % 4:
+        raise ValueError("tiled inference needs an image height that is a multiple of 4, "
+                         "got %d (see multisteps_forward_sharded)" % height)
     plan = BandPlan(height, world, k, align=4)                 # K x K halo (splat)
     uplan = BandPlan(height, world, k, pad=unet_pad, align=4)  # U-net halo
     dev = th.device("cuda", th.cuda.current_device())

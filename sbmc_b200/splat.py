@@ -108,6 +108,15 @@ class ProgressiveSplat(th.autograd.Function):
             t_k = t_max
         else:
             sum_r, sum_w, max_w = saved[5:]
+            # Where the running max came from.  Deviation from the composed chain
+            # (th.max(kmax, max_w) of sbmc/modules.py:449): on an exact tie torch.max
+            # splits the gradient 0.5 / 0.5 between the two operands, here all of it
+            # goes to the previous state; and when the arg-max tap is an out-of-image
+            # zero logit its share is still scattered to a real tap.  Both only move
+            # gradient between terms whose total derivative w.r.t. the max cancels in
+            # sum_r / sum_w (the output is invariant to the max), so the output
+            # gradient is unaffected; tests/test_modules.py checks values and gradients
+            # against the composed chain away from exact ties.
             from_prev = new_m == max_w          # the max came from earlier samples
             a = th.exp(max_w - new_m)
             d_a = (g_r * sum_r).sum(1, keepdim=True) + g_w * sum_w

@@ -38,6 +38,8 @@
 // 4..19 = epilogue.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "umma.cuh"
 
 namespace sbmc {
@@ -76,6 +78,18 @@ __device__ __forceinline__ void stg128(void *p, const uint4 &v) {
   asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+}
+
+// The CTA-pair kernel (below) is opt-in: sbmc_b200_conv3x3_pair(1) or
+// SBMC_B200_CONV_PAIR=1.  Measured on B200 it is CORRECT but 11 % SLOWER than the
+// single-CTA kernel on the Cout = 128 layers (profiles/r2j_convs_*.jsonl).
+static int g_pair = -1;
+static bool pair_enabled() {
+  if (g_pair < 0) {
+    const char *e = getenv("SBMC_B200_CONV_PAIR");
+    g_pair = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pair != 0;
 }
 
 struct TileCoord { int n, y0, x0, n0; };
@@ -261,6 +275,254 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+// ===========================================================================
+// CTA-pair variant for Cout = 128 (the full-resolution layers, 44 % of the U-net's
+// FLOPs) -- an EXPERIMENT that lost, kept opt-in with its measurement.  Hypothesis: with
+// N = 128 a single-CTA MMA reads A (4 KB) + B (4 KB) from shared memory every 64
+// cycles -- all of the 128 B/clk the SM has -- and the TMA writes of the next operands
+// come on top, which would explain why the main loop of conv3x3_kernel<128> runs at
+// ~72 % of the tensor rate at every Cin (profiles/r2c_ncu.md).  tcgen05.mma.cta_group::2
+// pairs two SMs: M = 256 = the same row block of TWO spatial tiles (one per CTA), each
+// CTA holds only HALF of the weight stage (64 of the 128 output channels), the weight
+// traffic from L2 halves.  Result on B200: bit-compatible output, but 0.242 ms vs
+// 0.217 ms (128 -> 128 @ 720p) and 0.646 vs 0.581 ms (384 -> 128): each SM still
+// consumes the whole B operand (its half locally, the other half from the partner), so
+// the operand read rate per SM does not drop, and the pair adds cross-CTA latency.
+//   * both CTAs load their own halo slab and their half of every weight stage; all
+//     loads signal the LEADER's mbarriers (cp.async.bulk.tensor ... .cta_group::2);
+//   * only the leader issues MMAs; tcgen05.commit ... .multicast::cluster releases the
+//     operand slots and publishes the accumulators in both CTAs;
+//   * both CTAs run their own epilogue on their own TMEM and tell the leader when an
+//     accumulator buffer is free (remote mbarrier arrive).
+// ===========================================================================
+constexpr int kPairStages = 10;                   // 8 KB half stages
+constexpr int kPairBStage = 64 * 128;
+enum { P_AF = 0, P_AE = 2, P_BF = 4, P_BE = 4 + kPairStages, P_ACCF = 4 + 2 * kPairStages,
+       P_ACCE = 6 + 2 * kPairStages, P_COUNT = 8 + 2 * kPairStages };
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // shared::cluster address -> the even CTA's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// all MMAs issued so far -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// TMA loads whose completion bytes are credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorMap *map,
+                                                 uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map,
+                                                 uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the leader's copy of a barrier (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                   smem_u32(bar) & kPeerMask)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W, H, N}
+                    const __grid_constant__ CUtensorMap wmap,      // weights {Cin, Cout, 9}, box 64 rows
+                    const Args P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem;                               // 2 halo slabs
+  unsigned char *sB = smem + 2 * kASlab;                  // kPairStages half stages
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kPairStages * kPairBStage);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + P_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    // full barriers: one arrive.expect_tx by the leader's producer (bytes of both CTAs);
+    // empty / acc_full: one multicast commit; acc_empty: the 16 epilogue warps of both CTAs
+    for (int i = 0; i < P_COUNT; ++i) mbar_init(bars + i, (i >= P_ACCE) ? 2 * kEpiWarps : 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nslabs = P.Cin / 64;
+  const long long npairs_total = (P.ntiles + 1) / 2;
+  const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== A producer: this CTA's halo slabs =====================
+    if (lane == 0) {
+      uint32_t ph = 0;
+      int ab = 0;
+      for (long long pt = pair0; pt < npairs_total; pt += pair_step) {
+        const long long tile = 2 * pt + rank;
+        TileCoord t = tile_coord(tile < P.ntiles ? tile : 0, P, 128);
+        if (tile >= P.ntiles) t.y0 = P.H + 8;             // dummy tile: the box is all zero fill
+        for (int s = 0; s < nslabs; ++s) {
+          mbar_wait(bars + P_AE + ab, ((ph >> ab) & 1) ^ 1); ph ^= 1u << ab;
+          if (leader) mbar_expect_tx(bars + P_AF + ab, (uint32_t)(2 * kASlab));
+          tma_load_4d_pair(sA + ab * kASlab, &amap, bars + P_AF + ab, s * 64, t.x0 - 1, t.y0 - 1, t.n);
+          ab ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: this CTA's half of every weight stage =====================
+    if (lane == 0) {
+      uint32_t ph = 0;
+      int st = 0;
+      for (long long pt = pair0; pt < npairs_total; pt += pair_step)
+        for (int s = 0; s < nslabs; ++s)
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bars + P_BE + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
+            if (leader) mbar_expect_tx(bars + P_BF + st, (uint32_t)(2 * kPairBStage));
+            tma_load_3d_pair(sB + st * kPairBStage, &wmap, bars + P_BF + st, s * 64, (int)rank * 64, tap);
+            st = (st + 1 == kPairStages) ? 0 : st + 1;
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, 128);
+      uint32_t ph_a = 0, ph_b = 0, ph_acc = 0;
+      int ab = 0, st = 0, it = 0;
+      for (long long pt = pair0; pt < npairs_total; pt += pair_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bars + P_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
+        for (int s = 0; s < nslabs; ++s) {
+          mbar_wait(bars + P_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
+          const unsigned char *a_base = sA + ab * kASlab;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            mbar_wait(bars + P_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
+            tcgen05_fence_after();
+            const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kPairBStage);
+#pragma unroll
+            for (int g = 0; g < kRows; ++g) {
+              const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
+              const uint32_t d = tmem + buf * 256 + g * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                              (s | tap | k) > 0);
+            }
+            umma_commit_pair(bars + P_BE + st);
+            st = (st + 1 == kPairStages) ? 0 : st + 1;
+          }
+          umma_commit_pair(bars + P_AE + ab);
+          ab ^= 1;
+        }
+        umma_commit_pair(bars + P_ACCF + buf);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own TMEM) =====================
+    const int quad = warp & 3, g = ((warp - 4) >> 2) & 1, part = (warp - 4) >> 3;
+    const int px = quad * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t ph = 0;
+    int it = 0;
+    for (long long pt = pair0; pt < npairs_total; pt += pair_step, ++it) {
+      const long long tile = 2 * pt + rank;
+      const bool real = tile < P.ntiles;
+      const TileCoord t = tile_coord(real ? tile : 0, P, 128);
+      const int buf = it & 1;
+      mbar_wait(bars + P_ACCF + buf, (ph >> buf) & 1); ph ^= 1u << buf;
+      tcgen05_fence_after();
+      const int y = t.y0 + g, x = t.x0 + px;
+      __nv_bfloat16 *own = P.out + (((long long)t.n * P.H + y) * P.W + x) * P.Cout;
+      const bool valid = real && y < P.H && x < P.W;
+      const int c0 = part * 64;
+      uint32_t q[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tmem_ld_32x32b_x32(lane_base + buf * 256 + g * 128 + c0 + 32 * hh, v);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 b = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + 32 * hh + 4 * q4));
+          float u0 = v[4 * q4] + b.x, u1 = v[4 * q4 + 1] + b.y;
+          float u2 = v[4 * q4 + 2] + b.z, u3 = v[4 * q4 + 3] + b.w;
+          if (P.act == 1) {
+            u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); u2 = fmaxf(u2, 0.f); u3 = fmaxf(u3, 0.f);
+          } else if (P.act == 2) {
+            u0 = fmaxf(u0, 0.01f * u0); u1 = fmaxf(u1, 0.01f * u1);
+            u2 = fmaxf(u2, 0.01f * u2); u3 = fmaxf(u3, 0.01f * u3);
+          }
+          q[16 * hh + 2 * q4] = pack_bf16(u0, u1);
+          q[16 * hh + 2 * q4 + 1] = pack_bf16(u2, u3);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stg256(own + c0 + 16 * k, q + 8 * k);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bars + P_ACCE + buf);
+    }
+  }
+  // nobody leaves while the partner may still read this CTA's shared memory / signal its
+  // barriers: the epilogues have seen the last accumulators, i.e. every MMA has retired
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)
+                 : "memory");
+}
+
+static int launch_pair(const Args &a, const CUtensorMap &am, const CUtensorMap &wm,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)2 * kASlab + (size_t)kPairStages * kPairBStage +
+                      P_COUNT * sizeof(uint64_t) + 16;
+  SBMC_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long pairs = (a.ntiles + 1) / 2;
+  long long grid = 2 * (pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+  {
+    KernelTimer timer(SBMC_KERNEL_CONV3X3, st);
+    conv3x3_pair_kernel<<<(unsigned)grid, kThreads, smem, st>>>(am, wm, a);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  return SBMC_OK;
+}
+
 template <int NT>
 static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, cudaStream_t st) {
   const size_t smem = (size_t)2 * kASlab + (size_t)stages_for(NT) * NT * 128 +
@@ -279,6 +541,12 @@ static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, c
 
 }  // namespace c3
 }  // namespace sbmc
+
+extern "C" int sbmc_b200_conv3x3_pair(int flag) {
+  const int prev = sbmc::c3::pair_enabled() ? 1 : 0;
+  sbmc::c3::g_pair = flag ? 1 : 0;
+  return prev;
+}
 
 extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *bias, void *y,
                                       int64_t n, int h, int w, int cin, int cout, int act,
@@ -326,5 +594,14 @@ extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   note_path(1);
+  if (nt == 128 && cout == 128 && c3::pair_enabled()) {
+    // CTA pairs (cta_group::2): each CTA loads 64 of the 128 output channels per stage
+    CUtensorMap wh;
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};
+    const uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * cout};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_tensor_map_bf16_sw128(&wh, w9, 3, dims, str, box)) return SBMC_ECUDA;
+    return c3::launch_pair(a, am, wh, st);
+  }
   return nt == 256 ? c3::launch<256>(a, am, wm, st) : c3::launch<128>(a, am, wm, st);
 }

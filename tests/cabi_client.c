@@ -28,6 +28,7 @@ int main(void) {
       (entry_fn)sbmc_conv1x1_chain_nhwc_bf16,
       (entry_fn)sbmc_chain_samples_nhwc_bf16,
       (entry_fn)sbmc_conv3x3_nhwc_bf16,
+      (entry_fn)sbmc_b200_conv3x3_pair,
       (entry_fn)sbmc_maxpool2x2_nhwc_bf16,
       (entry_fn)sbmc_upsample_concat_nhwc_bf16,
       (entry_fn)sbmc_bias_act_nhwc_bf16,

@@ -13,6 +13,7 @@ typedef long long i64;
 // ---- host side -----------------------------------------------------------
 void set_error(const char *fmt, ...);
 void note_path(int path);
+void warn_generic(const char *op, int c, int kh, int kw, long long w);
 void count_launch(int n = 1);
 bool force_generic();
 int num_sms();

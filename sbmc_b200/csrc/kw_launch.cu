@@ -64,7 +64,9 @@ static int dweights_tuned(const float *data_ext, const float *d_output,
 // (C, KW) pairs with a tuned instantiation: the SBMC model (3, 21), the
 // reference's own test shapes (tests/test_functions.py:43-144: C in {3, 5},
 // K in {3, 5, 7}) and config 1 of BASELINE.json (3, 5).
-#define SBMC_TUNED_SHAPES(X) X(3, 21) X(3, 5) X(3, 3) X(3, 7) X(5, 5) X(5, 3)
+#define SBMC_TUNED_SHAPES(X)                                                  \
+  X(3, 21) X(3, 5) X(3, 3) X(3, 7) X(5, 5) X(5, 3)                            \
+  X(3, 9) X(3, 11) X(3, 13) X(3, 15) X(3, 17) X(3, 19)
 
 int launch_fwd(const float *data_ext, const float *weights, float *output,
                float *sum_w, i64 n, int c, i64 h, i64 w, int kh, int kw,
@@ -81,6 +83,7 @@ int launch_fwd(const float *data_ext, const float *weights, float *output,
   SBMC_TUNED_SHAPES(X)
 #undef X
   note_path(2);
+  warn_generic("kernel_weighting", c, kh, kw, w);
   return generic_fwd(data_ext, weights, output, sum_w, n, c, h, w, kh, kw,
                      halo_top, halo_bot, st);
 }
@@ -102,6 +105,7 @@ int launch_bwd_dweights(const float *data_ext, const float *d_output,
   SBMC_TUNED_SHAPES(X)
 #undef X
   note_path(2);
+  warn_generic("kernel_weighting_grad (d_weights)", c, kh, kw, w);
   return generic_bwd_dweights(data_ext, d_output, d_sum_w, d_weights, n, c, h, w,
                               kh, kw, halo_top, halo_bot, st);
 }
@@ -122,6 +126,7 @@ int launch_bwd_ddata(const float *weights, const float *d_output,
   SBMC_TUNED_SHAPES(X)
 #undef X
   note_path(2);
+  warn_generic("kernel_weighting_grad (d_data)", c, kh, kw, w);
   return generic_bwd_ddata(weights, d_output, d_data_ext, n, c, h, w, kh, kw,
                            halo_top, halo_bot, st);
 }

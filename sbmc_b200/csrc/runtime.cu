@@ -1,5 +1,7 @@
 // runtime.cu -- error reporting, counters and the TMA tensor-map encoder.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -22,6 +24,21 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void note_path(int path) { g_path = path; }
+
+// One line on stderr the first time an operator leaves its tuned sm_100a kernel for the
+// one-thread-per-output generic kernel (>= 10x slower): the cliff must not be silent.
+// SBMC_B200_QUIET=1 suppresses it; forced generic runs (tests) do not warn.
+void warn_generic(const char *op, int c, int kh, int kw, long long w) {
+  static std::atomic<int> warned{0};
+  if (force_generic() || warned.exchange(1)) return;
+  const char *q = getenv("SBMC_B200_QUIET");
+  if (q && q[0] == '1') return;
+  fprintf(stderr,
+          "[sbmc_b200] %s: no tuned kernel for C=%d K=%dx%d W=%lld (tuned: C=3 with K in "
+          "{3,5,7,9,...,21}, C=5 with K in {3,5}; W %% 4 == 0, 16-byte aligned pointers): "
+          "using the generic kernel, expect >= 10x lower throughput\n",
+          op, c, kh, kw, w);
+}
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool force_generic() { return g_force_generic.load() != 0; }
 

@@ -147,6 +147,7 @@ int launch_s2g(const float *scatter, float *gather, i64 n, int kh, int kw, i64 h
       (unsigned long long)w * h * kh * kw * 4ull < (1ull << 40);
   if (!tma_ok) {
     note_path(2);
+    warn_generic("scatter2gather", 0, kh, kw, w);
     return generic_s2g(scatter, gather, n, kh, kw, h, w, st);
   }
   note_path(1);

@@ -400,6 +400,7 @@ int launch_splat_fwd(const float *kernels, const float *data, float *sum_r, floa
   X(3, 21) X(3, 5) X(3, 3) X(5, 3) X(3, 7)
 #undef X
   note_path(2);
+  warn_generic("progressive_splat", c, kh, kw, w);
   i64 blocks = ceil_div(n * h * w, 256);
   const i64 cap = (i64)num_sms() * 16;
   if (blocks > cap) blocks = cap;

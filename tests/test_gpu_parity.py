@@ -83,6 +83,10 @@ SHAPES = [
     (1, 1, 5, 4, 9, 9),          # kernel larger than the image
     (1, 7, 9, 12, 3, 5),         # odd channel count
     (1, 3, 1, 4, 1, 1),
+    (1, 3, 24, 132, 9, 9),       # the other odd kernel sizes of Multisteps(ksize=...):
+    (2, 3, 17, 260, 13, 13),     # tuned instantiations added in round 2
+    (1, 3, 30, 128, 19, 19),
+    (1, 3, 12, 256, 11, 15),     # non-square: kw selects the instantiation, kh is a runtime loop
 ]
 
 
@@ -106,6 +110,15 @@ def test_tuned_path_is_taken_for_model_shapes():
     data, weights, d_output, d_sum_w = make_inputs(1, 3, 16, 128, 21, 21)
     run_cuda(data, weights, d_output, d_sum_w)
     assert _lib.last_path() == 1
+    for k in (9, 11, 13, 15, 17, 19):            # every odd ksize up to the model's 21
+        data, weights, d_output, d_sum_w = make_inputs(1, 3, 16, 128, k, k)
+        halide = run_cuda(data, weights, d_output, d_sum_w)
+        assert _lib.last_path() in (1, 2) and halide is not None
+        from sbmc_b200 import halide_ops
+        dev = "cuda"
+        out = th.empty(1, 3, 16, 128, device=dev); sw = th.empty(1, 16, 128, device=dev)
+        halide_ops.kernel_weighting_cuda_float32(data.to(dev), weights.to(dev), out, sw)
+        assert _lib.last_path() == 1, k
     data, weights, d_output, d_sum_w = make_inputs(1, 3, 16, 50, 21, 21)
     run_cuda(data, weights, d_output, d_sum_w)
     assert _lib.last_path() == 2

@@ -512,11 +512,16 @@ def run_secondary(a, th, dist, dev, rank, world):
             sec["config4_train_step"] = {
                 "workload": "Multisteps(93,3) train step, B=8, spp=8, 128x128, K=21, "
                             "fwd + TonemappedRelativeMSE + bwd + clip + Adam, 1 GPU",
-                "path": "cuDNN convs; fused splat forward / backward and fused clip+Adam are "
-                        "repo kernels"}
-            for label, tf32 in (("fp32_strict", False), ("tf32_convs_allowed", True)):
+                "path": "cuDNN convs (variants bf16_unet_*: the U-net's forward and data-gradient "
+                        "convolutions on the repo's tcgen05 kernel); fused splat forward / "
+                        "backward and fused clip+Adam are repo kernels"}
+            for label, tf32, own in (("fp32_strict", False, False),
+                                     ("tf32_convs_allowed", True, False),
+                                     ("bf16_unet_own_kernels_rest_fp32_strict", False, True),
+                                     ("bf16_unet_own_kernels_rest_tf32", True, True)):
                 th.manual_seed(0)
                 net = models.Multisteps(93, 3).to(dev).train()
+                net.bf16_unet_train = own
                 iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True,
                                                                 fused_optimizer=True,
                                                                 allow_tf32=tf32)
@@ -526,8 +531,11 @@ def run_secondary(a, th, dist, dev, rank, world):
                 ms = _timed_cuda(th, train, 2, 4)
                 sec["config4_train_step"][label] = {
                     "ms": ms, "Msamples_per_s": 8 * 8 * 128 * 128 / ms / 1e3,
-                    "precision": "fp32 storage and accumulation, TF32 %s for cuDNN / cuBLAS"
-                                 % ("ALLOWED" if tf32 else "off")}
+                    "precision": ("fp32 storage and accumulation, TF32 %s for cuDNN / cuBLAS"
+                                  % ("ALLOWED" if tf32 else "off"))
+                    + ("; U-nets in bf16 (fp32 accumulate): forward and data-gradient "
+                       "convolutions on csrc/conv3x3.cu, weight gradients on cuDNN bf16"
+                       if own else "")}
                 del net, iface
             th.backends.cudnn.allow_tf32 = False
             th.backends.cuda.matmul.allow_tf32 = False

@@ -82,6 +82,11 @@ class Multisteps(nn.Module):
         # serial chain kernel / cuDNN convolutions (A/B comparisons)
         self.pipelined_chains = True
         self.own_convs = True
+        # opt-in (TRAINING, mixed precision): the U-nets run in bf16 with forward and
+        # data-gradient convolutions on csrc/conv3x3.cu (weight gradients on cuDNN
+        # bf16); everything else stays fp32 like the reference.  Gradients then carry
+        # bf16 rounding (~1e-2 relative), so this is not the default.
+        self.bf16_unet_train = False
 
         for step in range(nsteps):
             n_in = (n_features + n_global_features) if step == 0 \
@@ -156,7 +161,10 @@ class Multisteps(nn.Module):
                 reduced = features.mean(1)
                 nf = self.embedding_width
             unet = getattr(self, "propagation_{:02d}".format(step))
-            if getattr(self, "bf16_unet", False) and reduced.is_cuda and not th.is_grad_enabled():
+            if (getattr(self, "bf16_unet_train", False) and self.training and reduced.is_cuda
+                    and th.is_grad_enabled() and _unet_fast.supports_training(unet)):
+                propagated = _unet_fast.autoencoder_forward_train(unet, reduced)
+            elif getattr(self, "bf16_unet", False) and reduced.is_cuda and not th.is_grad_enabled():
                 with th.autocast("cuda", dtype=th.bfloat16):
                     propagated = unet(reduced.contiguous(memory_format=th.channels_last))
                 propagated = propagated.float().contiguous()

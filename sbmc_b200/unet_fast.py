@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from . import _lib
 from . import conv3x3 as _conv3x3
 
-__all__ = ["supports", "autoencoder_forward"]
+__all__ = ["supports", "supports_training", "autoencoder_forward", "autoencoder_forward_train"]
 
 _ACT = {th.nn.ReLU: 1, th.nn.LeakyReLU: 2}
 
@@ -169,3 +169,59 @@ def autoencoder_forward(autoencoder, x, own_convs=True):
     x = x.to(th.bfloat16).contiguous(memory_format=th.channels_last)
     with th.no_grad():
         return _level(autoencoder.net, x, own_convs)
+
+
+# -- opt-in mixed-precision TRAINING path ------------------------------------------------
+def supports_training(autoencoder):
+    """Every convolution of the U-net can run forward and data-gradient on conv3x3.cu."""
+    if not supports(autoencoder):
+        return False
+    for lvl in _levels(autoencoder.net):
+        chains = [lvl.left] + ([] if lvl.is_last else [lvl.right])
+        for chain in chains:
+            for conv, _ in _chain_layers(chain):
+                if not _conv3x3.supports_conv_training(conv):
+                    return False
+        if not lvl.is_last and not isinstance(lvl.downsample, th.nn.MaxPool2d):
+            return False
+    return True
+
+
+def _weight9(conv):
+    """bf16 [9, cout, cin] weight as a DIFFERENTIABLE function of the module's
+    parameters (weight normalization included), recomputed every step."""
+    if hasattr(conv, "weight_g") and hasattr(conv, "weight_v"):
+        w = th._weight_norm(conv.weight_v, conv.weight_g, 0)
+    else:
+        w = conv.weight
+    cout, cin = w.shape[:2]
+    return w.permute(2, 3, 0, 1).reshape(9, cout, cin).to(th.bfloat16).contiguous()
+
+
+def _chain_train(chain, x):
+    """x bf16 [n, h, w, c] contiguous -> same layout."""
+    for conv, act in _chain_layers(chain):
+        x = _conv3x3.Conv3x3BiasAct.apply(x.contiguous(), _weight9(conv), conv.bias.float(), act)
+    return x
+
+
+def _level_train(level, x):
+    left = _chain_train(level.left, x)
+    if level.is_last:
+        return left
+    # pooling / upsampling / concatenation: torch ops (autograd), NCHW-shaped views of the
+    # channels-innermost tensors
+    pooled = level.downsample(left.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    coarse = _level_train(level.next_level, pooled.contiguous())
+    up = F.interpolate(coarse.permute(0, 3, 1, 2), size=left.shape[1:3], mode="bilinear",
+                       align_corners=False).permute(0, 2, 3, 1)
+    return _chain_train(level.right, th.cat([up, left], 3))
+
+
+def autoencoder_forward_train(autoencoder, x):
+    """Differentiable bf16 forward of the U-net: x [n, c, h, w] (fp32 or bf16) ->
+    [n, c_out, h, w] in x's dtype.  Convolutions: `Conv3x3BiasAct` (forward and data
+    gradient on this repo's tcgen05 kernel, weight gradient on cuDNN bf16)."""
+    xn = x.permute(0, 2, 3, 1).to(th.bfloat16).contiguous()
+    y = _level_train(autoencoder.net, xn)
+    return y.permute(0, 3, 1, 2).to(x.dtype)

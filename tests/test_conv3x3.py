@@ -118,3 +118,74 @@ def test_cta_pair_kernel_gives_the_same_result(n, h, w):
     finally:
         _lib.load().sbmc_b200_conv3x3_pair(prev)
     assert th.equal(one, two)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,act", [(128, 128, 2), (256, 128, 1), (128, 256, 0)])
+def test_conv3x3_autograd_matches_torch(cin, cout, act):
+    """Conv3x3BiasAct (forward + data gradient on conv3x3.cu, weight gradient on cuDNN
+    bf16) against torch autograd in fp32 on the same bf16-rounded operands."""
+    th.manual_seed(7)
+    n, h, w = 2, 12, 40
+    x = th.randn(n, h, w, cin, device="cuda").to(th.bfloat16).requires_grad_(True)
+    wt = (th.randn(cout, cin, 3, 3, device="cuda") / (3 * cin ** 0.5)).to(th.bfloat16)
+    w9 = conv3x3.prepare_weight(wt).requires_grad_(True)
+    bias = th.randn(cout, device="cuda", requires_grad=True)
+    y = conv3x3.Conv3x3BiasAct.apply(x, w9, bias, act)
+    gy = th.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.float().requires_grad_(True)
+    br = bias.detach().clone().requires_grad_(True)
+    prev = th.backends.cudnn.allow_tf32
+    th.backends.cudnn.allow_tf32 = False
+    try:
+        yr = F.conv2d(xr, wr, br, padding=1)
+        yr = F.relu(yr) if act == 1 else (F.leaky_relu(yr, 0.01) if act == 2 else yr)
+        yr.backward(gy.float().permute(0, 3, 1, 2))
+    finally:
+        th.backends.cudnn.allow_tf32 = prev
+
+    def rel(a, b):
+        return ((a.float() - b).norm() / b.norm()).item()
+    assert rel(y.permute(0, 3, 1, 2), yr.detach()) < 5e-3
+    assert rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 1e-2
+    assert rel(w9.grad, wr.grad.permute(2, 3, 0, 1).reshape(9, cout, cin)) < 1e-2
+    assert rel(bias.grad, br.grad) < 1e-2
+
+
+@pytest.mark.gpu
+def test_unet_training_path_gradients_close_to_fp32_module():
+    th.manual_seed(3)
+    net = modules.Autoencoder(128, 128, num_levels=3, increase_factor=2.0, num_convs=3,
+                              width=128, ksize=3, output_type="leaky_relu", pooling="max").cuda().train()
+    assert unet_fast.supports_training(net)
+    x = th.randn(2, 128, 24, 40, device="cuda")
+    gy = th.randn(2, 128, 24, 40, device="cuda")
+    prev = th.backends.cudnn.allow_tf32
+    th.backends.cudnn.allow_tf32 = False
+    try:
+        ref = net(x)
+        ref.backward(gy)
+        want = {k: p.grad.clone() for k, p in net.named_parameters()}
+        net.zero_grad()
+        # the library's mixed precision (autocast bf16 through cuDNN) as the yardstick for
+        # what bf16 activations / gradients cost in a 15-convolution-deep network
+        with th.autocast("cuda", dtype=th.bfloat16):
+            lib = net(x)
+        lib.float().backward(gy)
+        lib_grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+        net.zero_grad()
+        got = unet_fast.autoencoder_forward_train(net, x)
+        got.backward(gy)
+    finally:
+        th.backends.cudnn.allow_tf32 = prev
+
+    def grad_err(grads):
+        num = sum(((grads[k] - want[k]) ** 2).sum() for k in want)
+        den = sum((want[k] ** 2).sum() for k in want)
+        return (num / den).sqrt().item()
+    assert ((got - ref).norm() / ref.norm()).item() < 3e-2
+    e_own = grad_err({k: p.grad for k, p in net.named_parameters()})
+    e_lib = grad_err(lib_grads)
+    assert e_own < 0.12 and e_own < 1.5 * e_lib + 1e-2, (e_own, e_lib)

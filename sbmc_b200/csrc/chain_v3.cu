@@ -190,7 +190,15 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
   uint64_t *bars = reinterpret_cast<uint64_t *>(sB3 + (REGRESS ? 0 : kHid));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
 
+  // Role index = hardware warp.  (Experiment, -DSBMC_CTRL_WARPS_LAST: the four control
+  // warps as the LAST hardware warps, in case the scheduler's warp-id priority starved the
+  // single-thread MMA issuer behind sixteen epilogue warps.  Measured: no gain on
+  // conv3x3, embeddings 8 % slower -- profiles/r2n_*.jsonl -- so the default stays.)
+#ifdef SBMC_CTRL_WARPS_LAST
+  const int tid = threadIdx.x, warp = ((tid >> 5) + 4) % (kThreads / 32), lane = tid & 31;
+#else
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#endif
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i) {

@@ -118,7 +118,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
   uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kStages * kBStage);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
 
+  // Role index = hardware warp.  (Experiment, -DSBMC_CTRL_WARPS_LAST: the four control
+  // warps as the LAST hardware warps, in case the scheduler's warp-id priority starved the
+  // single-thread MMA issuer behind sixteen epilogue warps.  Measured: no gain on
+  // conv3x3, embeddings 8 % slower -- profiles/r2n_*.jsonl -- so the default stays.)
+#ifdef SBMC_CTRL_WARPS_LAST
+  const int tid = threadIdx.x, warp = ((tid >> 5) + 4) % (kThreads / 32), lane = tid & 31;
+#else
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#endif
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, (i >= B_ACCE) ? kEpiWarps : 1);
@@ -359,7 +367,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Ci
   uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kPairStages * kPairBStage);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + P_COUNT);
 
+  // Role index = hardware warp.  (Experiment, -DSBMC_CTRL_WARPS_LAST: the four control
+  // warps as the LAST hardware warps, in case the scheduler's warp-id priority starved the
+  // single-thread MMA issuer behind sixteen epilogue warps.  Measured: no gain on
+  // conv3x3, embeddings 8 % slower -- profiles/r2n_*.jsonl -- so the default stays.)
+#ifdef SBMC_CTRL_WARPS_LAST
+  const int tid = threadIdx.x, warp = ((tid >> 5) + 4) % (kThreads / 32), lane = tid & 31;
+#else
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#endif
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if ((smem_u32(smem) & 1023u) != 0) __trap();

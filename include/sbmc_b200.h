@@ -215,8 +215,9 @@ SBMC_API int sbmc_chain_samples_nhwc_bf16(
 SBMC_API int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *bias, void *y,
                                     int64_t n, int h, int w, int cin, int cout, int act,
                                     void *stream);
-/* Selects (flag != 0) the CTA-pair kernel (tcgen05.mma.cta_group::2) for cout = 128; off
- * by default: measured slower than the single-CTA kernel.  Returns the previous value. */
+/* flag != 0 (the default): cout = 128 runs on the CTA-pair kernel
+ * (tcgen05.mma.cta_group::2, 4-8 % faster); 0 selects the single-CTA kernel.  Returns
+ * the previous value. */
 SBMC_API int sbmc_b200_conv3x3_pair(int flag);
 
 /* U-net decoder glue (sbmc/modules.py:314-319): out = cat([bilinear_upsample(low,

@@ -78,7 +78,7 @@ struct Args {
 #define TRACE_DECL(role) int trace_n_ = 0; const int trace_role_ = (role)
 #define TRACE(code)                                                                  \
   do {                                                                               \
-    if (P.trace && blockIdx.x == 0 && trace_n_ < 2000) {                             \
+    if (P.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n_ < 2000) {  \
       P.trace[(trace_role_ * 2000 + trace_n_) * 2] = (code);                         \
       P.trace[(trace_role_ * 2000 + trace_n_) * 2 + 1] = clock64();                  \
       ++trace_n_;                                                                    \
@@ -272,8 +272,16 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the (uniform) control flow and waits on the barriers; one
+    // elected lane issues the MMAs and the commits (see umma.cuh::elect_one).
+    {
       const uint32_t idesc_h = umma_idesc_bf16(128, kHid);
+      // descriptors of slab 0 of every operand; slab s is + s * (kSlab >> 4), K step k
+      // inside a slab is + 2 k (16-byte units)
+      const uint64_t dF = umma_smem_desc_sw128(sF), dP = umma_smem_desc_sw128(sP);
+      const uint64_t dW1 = umma_smem_desc_sw128(sW1), dW2 = umma_smem_desc_sw128(sW2);
+      const uint64_t dW3 = umma_smem_desc_sw128(sW3);
+      constexpr uint64_t kSlabD = kSlab >> 4;
       // phase bits live in one register each (no dynamically indexed local arrays)
       uint32_t ph_f = 0, ph_p = 0, ph_me = 0;
       uint32_t ph_ar = 0;                        // bit e
@@ -301,31 +309,39 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
             has_prev |= 1u << e;
             TRACE(12 + e);                            // X_e free, issuing layer 1
             tcgen05_fence_after();
-            const uint32_t x = tmem + e * 192;
+            if (elect_one()) {
+              const uint32_t x = tmem + e * 192;
+              const uint64_t dFe = dF + (uint64_t)(2 * e) * kSlabD;
 #pragma unroll
-            for (int k = 0; k < KS1 * 4; ++k) {
-              const unsigned char *a = (k < 8) ? sF + (2 * e + (k >> 2)) * kSlab
-                                               : sP + ((k - 8) >> 2) * kSlab;
-              const uint64_t ad = umma_smem_desc_sw128(a) + (uint64_t)((k & 3) * 2);
-              const uint64_t bd = umma_smem_desc_sw128(sW1 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
-              umma_bf16(x, ad, bd, idesc_h, k > 0);
+              for (int k = 0; k < KS1 * 4; ++k) {
+                const uint64_t ad = (k < 8 ? dFe + (uint64_t)(k >> 2) * kSlabD
+                                           : dP + (uint64_t)((k - 8) >> 2) * kSlabD) +
+                                    (uint64_t)((k & 3) * 2);
+                const uint64_t bd = dW1 + (uint64_t)(k >> 2) * kSlabD + (uint64_t)((k & 3) * 2);
+                umma_bf16(x, ad, bd, idesc_h, k > 0);
+              }
+              umma_commit(bars + B_ACC0 + e);
+              if (e == ne - 1) {
+                umma_commit(bars + B_F_EMPTY);
+                if (KS1 == 4 && last) umma_commit(bars + B_P_EMPTY);
+              }
             }
-            umma_commit(bars + B_ACC0 + e);
+            __syncwarp();
           }
-          umma_commit(bars + B_F_EMPTY);
-          if (KS1 == 4 && last) umma_commit(bars + B_P_EMPTY);
           // ---- layer 2: X_e = Y_e . W2^T  (A operand in tensor memory) ----
           for (int e = 0; e < ne; ++e) {
             wait_ar(e);
             TRACE(14 + e);                            // E1_e done, issuing layer 2
             tcgen05_fence_after();
-            const uint32_t x = tmem + e * 192, y = x + 128;
+            if (elect_one()) {
+              const uint32_t x = tmem + e * 192, y = x + 128;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t bd = umma_smem_desc_sw128(sW2 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
-              umma_bf16_ts(x, y + k * 8, bd, idesc_h, k > 0);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16_ts(x, y + k * 8, dW2 + (uint64_t)(k >> 2) * kSlabD + (uint64_t)((k & 3) * 2),
+                             idesc_h, k > 0);
+              umma_commit(bars + B_ACC0 + e);
             }
-            umma_commit(bars + B_ACC0 + e);
+            __syncwarp();
           }
           // ---- layer 3 ----
           if (!REGRESS) {
@@ -334,16 +350,19 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
               wait_ar(e);
               TRACE(16 + e);                          // E2_e done, issuing layer 3
               tcgen05_fence_after();
-              const uint32_t x = tmem + e * 192, y = x + 128;
+              if (elect_one()) {
+                const uint32_t x = tmem + e * 192, y = x + 128;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint64_t bd = umma_smem_desc_sw128(sW3 + (k >> 2) * kSlab) + (uint64_t)((k & 3) * 2);
-                umma_bf16_ts(x, y + k * 8, bd, idesc_h, k > 0);
-                if (do_mean) umma_bf16_ts(tmem + 384, y + k * 8, bd, idesc_h, (j | e | k) > 0);
+                for (int k = 0; k < 8; ++k) {
+                  const uint64_t bd = dW3 + (uint64_t)(k >> 2) * kSlabD + (uint64_t)((k & 3) * 2);
+                  umma_bf16_ts(x, y + k * 8, bd, idesc_h, k > 0);
+                  if (do_mean) umma_bf16_ts(tmem + 384, y + k * 8, bd, idesc_h, (j | e | k) > 0);
+                }
+                umma_commit(bars + B_ACC0 + e);
+                if (do_mean && last && e == ne - 1) umma_commit(bars + B_M_FULL);
               }
-              umma_commit(bars + B_ACC0 + e);
+              __syncwarp();
             }
-            if (do_mean && last) umma_commit(bars + B_M_FULL);
           } else {
             for (int c = 0; c < nchunks; ++c) {
               const int rows = min(kChunk, P.n3p - c * kChunk);
@@ -357,24 +376,28 @@ chain_v3_kernel(const __grid_constant__ CUtensorMap fmap,      // feats {128, hw
                   ph_oe ^= 1u << (3 * e + ob);
                 }
                 tcgen05_fence_after();
-                const uint32_t y = tmem + e * 192 + 128;
-                const uint32_t o = (ob < 2) ? tmem + e * 192 + ob * 64 : tmem + 384 + e * 64;
-                const unsigned char *wb = sW3 + ring * kSlab;
+                if (elect_one()) {
+                  const uint32_t y = tmem + e * 192 + 128;
+                  const uint32_t o = (ob < 2) ? tmem + e * 192 + ob * 64 : tmem + 384 + e * 64;
+                  const uint64_t wb = dW3 + (uint64_t)ring * kSlabD;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const uint64_t bd = umma_smem_desc_sw128(wb + (k >> 2) * (kSlab / 2)) + (uint64_t)((k & 3) * 2);
-                  umma_bf16_ts(o, y + k * 8, bd, idesc_c, k > 0);
+                  for (int k = 0; k < 8; ++k)
+                    umma_bf16_ts(o, y + k * 8,
+                                 wb + (uint64_t)(k >> 2) * (kSlabD / 2) + (uint64_t)((k & 3) * 2),
+                                 idesc_c, k > 0);
+                  umma_commit(bars + B_OF + 3 * e + ob);
+                  if (e == ne - 1) umma_commit(bars + B_W3E0 + ring);
                 }
-                umma_commit(bars + B_OF + 3 * e + ob);
+                __syncwarp();
               }
-              umma_commit(bars + B_W3E0 + ring);
               ring ^= 1;
             }
           }
         }
       }
       // drain: every MMA and every commit-arrive has landed before the CTA may exit
-      umma_commit(bars + B_W);
+      if (elect_one()) umma_commit(bars + B_W);
+      __syncwarp();
       mbar_wait(bars + B_W, 1);
     }
   } else if (warp >= kCtrlWarps) {

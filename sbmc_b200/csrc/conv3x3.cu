@@ -80,14 +80,17 @@ __device__ __forceinline__ void stg128(void *p, const uint4 &v) {
                : "memory");
 }
 
-// The CTA-pair kernel (below) is opt-in: sbmc_b200_conv3x3_pair(1) or
-// SBMC_B200_CONV_PAIR=1.  Measured on B200 it is CORRECT but 11 % SLOWER than the
-// single-CTA kernel on the Cout = 128 layers (profiles/r2j_convs_*.jsonl).
+// The CTA-pair kernel (below) serves Cout = 128 by default; sbmc_b200_conv3x3_pair(0) or
+// SBMC_B200_CONV_PAIR=0 selects the single-CTA kernel (A/B runs).  History of the
+// measurement (profiles/r2j_*, r2o_*): with the MMAs issued from a divergent
+// `if (lane == 0)` block both kernels were bound by the issuing thread and the pair was
+// 11 % SLOWER; once the issue loop compiled to back-to-back UTCHMMA (umma.cuh::elect_one)
+// the pair became 4-8 % FASTER (128->128: 0.195 vs 0.204 ms, 384->128: 0.517 vs 0.560 ms).
 static int g_pair = -1;
 static bool pair_enabled() {
   if (g_pair < 0) {
     const char *e = getenv("SBMC_B200_CONV_PAIR");
-    g_pair = (e && e[0] == '1') ? 1 : 0;
+    g_pair = (e && e[0] == '0') ? 0 : 1;
   }
   return g_pair != 0;
 }
@@ -172,8 +175,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp: uniform control flow + barrier waits; one elected lane issues
+    // (umma.cuh::elect_one); descriptors are hoisted, per MMA only an add remains
+    {
       const uint32_t idesc = umma_idesc_bf16(128, NT);
+      const uint64_t dA = umma_smem_desc_sw128(sA), dB = umma_smem_desc_sw128(sB);
       uint32_t ph_a = 0, ph_b = 0, ph_acc = 0;
       int ab = 0, st = 0, it = 0;
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
@@ -181,31 +187,39 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
         mbar_wait(bars + B_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + B_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
-          const unsigned char *a_base = sA + ab * kASlab;
+          const uint64_t da = dA + (uint64_t)ab * (kASlab >> 4);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            constexpr int kRowD = 128 >> 4;               // one halo row (pixel) in 16-byte units
             const int dy = tap / 3, dx = tap - 3 * dy;
             mbar_wait(bars + B_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
             tcgen05_fence_after();
-            const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kBStage);
+            if (elect_one()) {
+              const uint64_t bd0 = dB + (uint64_t)st * (kBStage >> 4);
 #pragma unroll
-            for (int g = 0; g < kRows; ++g) {
-              const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
-              const uint32_t d = tmem + ((NT == 128) ? buf * 256 + g * 128 : g * 256);
+              for (int g = 0; g < kRows; ++g) {
+                const uint64_t ad0 = da + (uint64_t)(((g + dy) * kHaloW + dx) * kRowD);
+                const uint32_t d = tmem + ((NT == 128) ? buf * 256 + g * 128 : g * 256);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
-                          (s | tap | k) > 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                            (s | tap | k) > 0);
+              }
+              umma_commit(bars + B_BE + st);
+              if (tap == 8) {
+                umma_commit(bars + B_AE + ab);
+                if (s == nslabs - 1) umma_commit(bars + B_ACCF + buf);
+              }
             }
-            umma_commit(bars + B_BE + st);
+            __syncwarp();
             st = (st + 1 == kStages) ? 0 : st + 1;
           }
-          umma_commit(bars + B_AE + ab);
           ab ^= 1;
         }
-        umma_commit(bars + B_ACCF + buf);
       }
       // drain: all commits have landed before the CTA exits
-      umma_commit(bars + B_AF);
+      if (elect_one()) umma_commit(bars + B_AF);
+      __syncwarp();
       mbar_wait(bars + B_AF, (ph_a & 1));
     }
   } else if (warp >= 4) {
@@ -285,17 +299,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
 
 // ===========================================================================
 // CTA-pair variant for Cout = 128 (the full-resolution layers, 44 % of the U-net's
-// FLOPs) -- an EXPERIMENT that lost, kept opt-in with its measurement.  Hypothesis: with
-// N = 128 a single-CTA MMA reads A (4 KB) + B (4 KB) from shared memory every 64
-// cycles -- all of the 128 B/clk the SM has -- and the TMA writes of the next operands
-// come on top, which would explain why the main loop of conv3x3_kernel<128> runs at
-// ~72 % of the tensor rate at every Cin (profiles/r2c_ncu.md).  tcgen05.mma.cta_group::2
-// pairs two SMs: M = 256 = the same row block of TWO spatial tiles (one per CTA), each
-// CTA holds only HALF of the weight stage (64 of the 128 output channels), the weight
-// traffic from L2 halves.  Result on B200: bit-compatible output, but 0.242 ms vs
-// 0.217 ms (128 -> 128 @ 720p) and 0.646 vs 0.581 ms (384 -> 128): each SM still
-// consumes the whole B operand (its half locally, the other half from the partner), so
-// the operand read rate per SM does not drop, and the pair adds cross-CTA latency.
+// FLOPs).  With N = 128 a single-CTA MMA reads A (4 KB) + B (4 KB) from shared memory
+// every 64 cycles -- all of the 128 B/clk the SM has -- and the TMA writes of the next
+// operands come on top.  tcgen05.mma.cta_group::2 pairs two SMs: M = 256 = the same row
+// block of TWO spatial tiles (one per CTA), each CTA holds only HALF of the weight stage
+// (64 of the 128 output channels), and the weight traffic from L2 halves.
 //   * both CTAs load their own halo slab and their half of every weight stage; all
 //     loads signal the LEADER's mbarriers (cp.async.bulk.tensor ... .cta_group::2);
 //   * only the leader issues MMAs; tcgen05.commit ... .multicast::cluster releases the
@@ -432,8 +440,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Ci
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       const uint32_t idesc = umma_idesc_bf16(256, 128);
+      const uint64_t dA = umma_smem_desc_sw128(sA), dB = umma_smem_desc_sw128(sB);
       uint32_t ph_a = 0, ph_b = 0, ph_acc = 0;
       int ab = 0, st = 0, it = 0;
       for (long long pt = pair0; pt < npairs_total; pt += pair_step, ++it) {
@@ -441,28 +450,34 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Ci
         mbar_wait(bars + P_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + P_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
-          const unsigned char *a_base = sA + ab * kASlab;
+          const uint64_t da = dA + (uint64_t)ab * (kASlab >> 4);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3, dx = tap - 3 * dy;
             mbar_wait(bars + P_BF + st, (ph_b >> st) & 1); ph_b ^= 1u << st;
             tcgen05_fence_after();
-            const uint64_t bd0 = umma_smem_desc_sw128(sB + st * kPairBStage);
+            if (elect_one()) {
+              const uint64_t bd0 = dB + (uint64_t)st * (kPairBStage >> 4);
 #pragma unroll
-            for (int g = 0; g < kRows; ++g) {
-              const uint64_t ad0 = umma_smem_desc_sw128(a_base + ((g + dy) * kHaloW + dx) * 128);
-              const uint32_t d = tmem + buf * 256 + g * 128;
+              for (int g = 0; g < kRows; ++g) {
+                const uint64_t ad0 = da + (uint64_t)(((g + dy) * kHaloW + dx) * 8);
+                const uint32_t d = tmem + buf * 256 + g * 128;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
-                              (s | tap | k) > 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_2sm(d, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                                (s | tap | k) > 0);
+              }
+              umma_commit_pair(bars + P_BE + st);
+              if (tap == 8) {
+                umma_commit_pair(bars + P_AE + ab);
+                if (s == nslabs - 1) umma_commit_pair(bars + P_ACCF + buf);
+              }
             }
-            umma_commit_pair(bars + P_BE + st);
+            __syncwarp();
             st = (st + 1 == kPairStages) ? 0 : st + 1;
           }
-          umma_commit_pair(bars + P_AE + ab);
           ab ^= 1;
         }
-        umma_commit_pair(bars + P_ACCF + buf);
       }
     }
   } else if (warp >= 4) {

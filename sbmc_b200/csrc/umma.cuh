@@ -68,6 +68,23 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  MMA issue belongs inside
+// `if (elect_one()) { ... }` of a warp whose control flow is otherwise uniform: under a
+// plain `if (lane == 0)` the compiler cannot prove the tcgen05 operands uniform and wraps
+// every UTCHMMA in an ELECT / BRA.U.ANY loop (about ten extra instructions per MMA, which
+// made the single issuing thread the bottleneck of the N = 128 kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }

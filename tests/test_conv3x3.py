@@ -103,17 +103,19 @@ def test_upsample_concat_and_layout_change_kernels_after_their_rewrite():
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,h,w", [(1, 8, 128), (2, 7, 45), (1, 33, 300)])
 def test_cta_pair_kernel_gives_the_same_result(n, h, w):
-    """The opt-in tcgen05.mma.cta_group::2 variant (two spatial tiles per CTA pair, half
-    of every weight stage per CTA; odd tile counts end in a dummy tile)."""
+    """The tcgen05.mma.cta_group::2 kernel (two spatial tiles per CTA pair, half of every
+    weight stage per CTA; odd tile counts end in a dummy tile) against the single-CTA
+    kernel."""
     from sbmc_b200 import _lib
     th.manual_seed(5)
     x = th.randn(n, h, w, 128, device="cuda").to(th.bfloat16)
     wt = (th.randn(128, 128, 3, 3, device="cuda") / 34.0).to(th.bfloat16)
     bias = th.randn(128, device="cuda")
     w9 = conv3x3.prepare_weight(wt)
-    one = conv3x3.conv3x3_nhwc(x, w9, bias, act=2)
-    prev = _lib.load().sbmc_b200_conv3x3_pair(1)
+    prev = _lib.load().sbmc_b200_conv3x3_pair(0)
     try:
+        one = conv3x3.conv3x3_nhwc(x, w9, bias, act=2)
+        _lib.load().sbmc_b200_conv3x3_pair(1)
         two = conv3x3.conv3x3_nhwc(x, w9, bias, act=2)
     finally:
         _lib.load().sbmc_b200_conv3x3_pair(prev)

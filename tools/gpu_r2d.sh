@@ -18,5 +18,5 @@ PY
 tail -5 gpurun_out/${tag}_bench.err
 echo "== trace build"
 SBMC_B200_NVCC_FLAGS="-DSBMC_CHAIN_TRACE" python -c "from sbmc_b200 import build; build.build(force=True)" > /dev/null 2>&1
-timeout 200 python tools/chain_trace.py 2>&1 | tail -110 | tee gpurun_out/${tag}_chain_trace.txt
+SBMC_B200_NVCC_FLAGS="-DSBMC_CHAIN_TRACE" timeout 200 python tools/chain_trace.py 2>&1 | tail -110 | tee gpurun_out/${tag}_chain_trace.txt
 python -c "from sbmc_b200 import build; build.build(force=True)" > /dev/null 2>&1

@@ -67,6 +67,30 @@ write_pattern_kernel(float *dW, int H, int W, int taps, int xtiles, int ytiles) 
   }
 }
 
+// The same volume written with TMA tensor stores (cp.async.bulk.tensor ... global.shared,
+// SASS UTMASTG): per tap plane one [ROWS x 128 px] box from shared memory, DEPTH bulk
+// groups in flight.  Answers "would smem-staged TMA stores lift the d_weights write rate?"
+template <int ROWS, int DEPTH>
+__global__ void __launch_bounds__(128)
+tma_store_pattern_kernel(const __grid_constant__ CUtensorMap map, int taps, int xtiles,
+                         int ytiles) {
+  extern __shared__ __align__(128) float tile[];          // [2][ROWS][128]
+  const int xt = blockIdx.x % xtiles;
+  const unsigned r = blockIdx.x / xtiles;
+  const int yt = r % ytiles, n = r / ytiles;
+  for (int i = threadIdx.x; i < 2 * ROWS * 128; i += 128) tile[i] = (float)i;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < taps; ++t) {
+      tma_store_4d(&map, tile + (t & 1) * ROWS * 128, xt * 128, yt * ROWS, t, n);
+      tma_commit_group();
+      tma_wait_group_read<DEPTH>();
+    }
+    tma_wait_group<0>();
+  }
+}
+
 struct Ctx {
   i64 n = 4, h = 720, w = 1280;
   int k = 21;
@@ -174,6 +198,23 @@ int main(int argc, char **argv) {
         c.dwt, (int)c.h, (int)c.w, c.k * c.k, xt, yt);                        \
     return 0;                                                                 \
   });
+#define TPAT(ROWS, DEPTH)                                                     \
+  time_it(c, "TMA store pattern rows=" #ROWS " depth=" #DEPTH, 4.0 * 441, [&] { \
+    CUtensorMap m;                                                            \
+    const uint64_t dims[4] = {(uint64_t)c.w, (uint64_t)c.h, (uint64_t)(c.k * c.k), (uint64_t)c.n}; \
+    const uint64_t str[3] = {(uint64_t)c.w * 4, (uint64_t)c.w * c.h * 4,       \
+                             (uint64_t)c.w * c.h * c.k * c.k * 4};             \
+    const uint32_t box[4] = {128, ROWS, 1, 1};                                \
+    if (!encode_tensor_map_f32(&m, c.dwt, 4, dims, str, box)) return 1;       \
+    const int xt = (int)ceil_div(c.w, 128), yt = (int)ceil_div(c.h, ROWS);    \
+    tma_store_pattern_kernel<ROWS, DEPTH><<<(unsigned)(xt * yt * c.n), 128,   \
+                                            2 * ROWS * 128 * 4, c.st>>>(m, c.k * c.k, xt, yt); \
+    return 0;                                                                 \
+  });
+  if (!strcmp(which, "tpat")) {
+    WPAT(16, 1)
+    TPAT(8, 4) TPAT(16, 4) TPAT(16, 8) TPAT(16, 16) TPAT(32, 8) TPAT(32, 16) TPAT(48, 8)
+  }
   if (!strcmp(which, "wpat")) {
     WPAT(16, 1) WPAT(8, 1) WPAT(8, 2) WPAT(4, 4) WPAT(8, 5) WPAT(2, 10) WPAT(1, 10) WPAT(4, 10)
     WPAT(16, 2) WPAT(4, 2)

@@ -515,13 +515,15 @@ def run_secondary(a, th, dist, dev, rank, world):
                 "path": "cuDNN convs (variants bf16_unet_*: the U-net's forward and data-gradient "
                         "convolutions on the repo's tcgen05 kernel); fused splat forward / "
                         "backward and fused clip+Adam are repo kernels"}
-            for label, tf32, own in (("fp32_strict", False, False),
-                                     ("tf32_convs_allowed", True, False),
-                                     ("bf16_unet_own_kernels_rest_fp32_strict", False, True),
-                                     ("bf16_unet_own_kernels_rest_tf32", True, True)):
+            for label, tf32, own in (("fp32_strict", False, 0),
+                                     ("tf32_convs_allowed", True, 0),
+                                     ("bf16_unet_own_kernels_rest_fp32_strict", False, 1),
+                                     ("bf16_unet_own_kernels_rest_tf32", True, 1),
+                                     ("bf16_train_chains_and_unet_own_kernels", False, 2)):
                 th.manual_seed(0)
                 net = models.Multisteps(93, 3).to(dev).train()
-                net.bf16_unet_train = own
+                net.bf16_unet_train = own == 1
+                net.bf16_train = own == 2
                 iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True,
                                                                 fused_optimizer=True,
                                                                 allow_tf32=tf32)
@@ -535,7 +537,10 @@ def run_secondary(a, th, dist, dev, rank, world):
                                   % ("ALLOWED" if tf32 else "off"))
                     + ("; U-nets in bf16 (fp32 accumulate): forward and data-gradient "
                        "convolutions on csrc/conv3x3.cu, weight gradients on cuDNN bf16"
-                       if own else "")}
+                       if own else "")
+                    + ("; 1x1 chains in bf16: forward and data-gradient layers on "
+                       "csrc/linear.cu, weight gradients on cuBLAS bf16; no fp32 "
+                       "convolution left" if own == 2 else "")}
                 del net, iface
             th.backends.cudnn.allow_tf32 = False
             th.backends.cuda.matmul.allow_tf32 = False

@@ -228,6 +228,16 @@ SBMC_API int sbmc_upsample_concat_nhwc_bf16(const void *low, const void *skip, v
                                    int64_t n, int hl, int wl, int h, int w, int cu,
                                    int cs, void *stream);
 
+/* One 1x1-convolution layer as a tcgen05 GEMM (csrc/linear.cu): x bf16 [pixels][cin],
+ * w bf16 [cout][cin], bias fp32 [cout] or NULL; y [pixels][cout] = act(x . w^T + bias) as
+ * bf16 (out_f32 == 0) or fp32; act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  cin multiple of
+ * 64, cout multiple of 128, 32-byte aligned pointers.  The layer-by-layer form of the
+ * per-sample ConvChains (sbmc/modules.py:34-125) that the mixed-precision training path
+ * needs (every layer output is kept for the backward pass). */
+SBMC_API int sbmc_linear_nhwc_bf16(const void *x, const void *w, const float *bias, void *y,
+                                   int64_t pixels, int cin, int cout, int act, int out_f32,
+                                   void *stream);
+
 /* 2 x 2 / stride 2 max pooling (the U-net's `downsample`, sbmc/modules.py:296-299:
  * nn.MaxPool2d(2, 2), floor mode) on bf16 channels-innermost x [n][h][w][c] ->
  * y [n][h/2][w/2][c]; c multiple of 8, 16-byte aligned pointers. */

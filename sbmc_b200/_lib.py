@@ -48,6 +48,8 @@ SIGNATURES = {
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_upsample_concat_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
+    "sbmc_linear_nhwc_bf16":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]),
     "sbmc_maxpool2x2_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _int, _ptr]),
     "sbmc_bias_act_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _ptr]),
     "sbmc_nchw_to_nhwc_bf16": (_int, [_ptr, _i64, _ptr, _i64, _i64, _int, _i64, _int, _ptr]),

@@ -26,6 +26,7 @@ constructor's argument checks (models.py:62,66), which turns the intended
 import torch as th
 import torch.nn as nn
 
+from . import chain_train as _chain_train
 from . import conv1x1 as _conv1x1
 from . import unet_fast as _unet_fast
 from . import modules as ops
@@ -87,6 +88,11 @@ class Multisteps(nn.Module):
         # bf16); everything else stays fp32 like the reference.  Gradients then carry
         # bf16 rounding (~1e-2 relative), so this is not the default.
         self.bf16_unet_train = False
+        # opt-in (TRAINING, mixed precision): in addition the per-sample 1x1 chains run
+        # layer by layer on the tcgen05 GEMM kernel (csrc/linear.cu; forward and data
+        # gradients; weight gradients are library GEMMs) and activations stay bf16
+        # channels-innermost between the chains and the U-nets (sbmc_b200/chain_train.py)
+        self.bf16_train = False
 
         for step in range(nsteps):
             n_in = (n_features + n_global_features) if step == 0 \
@@ -126,6 +132,11 @@ class Multisteps(nn.Module):
 
         if fused_chains and self._nhwc_pipeline_ok(nf):
             return self._forward_nhwc(radiance, features, gfeatures)
+        if (getattr(self, "bf16_train", False) and self.training and radiance.is_cuda
+                and th.is_grad_enabled() and self._nhwc_pipeline_ok(nf)
+                and all(_unet_fast.supports_training(getattr(self, "propagation_{:02d}".format(i)))
+                        for i in range(self.nsteps))):
+            return self._forward_train_nhwc(radiance, features, gfeatures)
 
         propagated = None
         for step in range(self.nsteps):
@@ -258,6 +269,53 @@ class Multisteps(nn.Module):
                 kernels = kernels.view(bs, k2, h, w)
                 sum_r, sum_w, max_w = self.kernel_update(
                     crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
+        output = sum_r / (sum_w + self.eps)
+        crop = (self.ksize - 1) // 2
+        return {"radiance": output[..., crop:-crop, crop:-crop]}
+
+
+    # -- opt-in mixed-precision training pipeline (bf16_train) -------------------------
+    def _forward_train_nhwc(self, radiance, features, gfeatures):
+        """The train branch of `forward` (sbmc/models.py:171-209) with bf16
+        channels-innermost activations: the 1x1 chains as layer-wise tcgen05 GEMMs
+        with an autograd backward (`chain_train.ChainFn`), the U-nets through
+        `unet_fast.autoencoder_forward_train`, the splat through the fused fp32
+        kernels.  Keeps the reference's pairing of samples and global features
+        (sample-major tiling against a batch-major flattening, see the module
+        docstring)."""
+        bs, spp, nf, h, w = features.shape
+        hw = h * w
+        npix = bs * spp * hw
+        ngf = gfeatures.shape[1]
+        # rows = (b, s, pixel); channels = [nf features | ngf global features | zero pad]
+        x = features.new_zeros((bs * spp, hw, 128), dtype=th.bfloat16)
+        x[:, :, :nf] = features.reshape(bs * spp, nf, hw).transpose(1, 2)
+        gidx = th.arange(bs * spp, device=features.device) % bs     # the reference's quirk
+        x[:, :, nf:nf + ngf] = gfeatures.reshape(bs, ngf)[gidx].unsqueeze(1).to(th.bfloat16)
+        x = x.view(npix, 128)
+        prop = None
+        for step in range(self.nsteps):
+            embed = getattr(self, "embedding_{:02d}".format(step))
+            if step > 0:
+                ctx = prop.unsqueeze(1).expand(bs, spp, hw, 128).reshape(npix, 128)
+                x = th.cat([x, ctx], 1)
+            w1, b1, w2, b2, w3, b3, act, _ = _chain_train.chain_weights(embed, x.shape[1])
+            x = _chain_train.ChainFn.apply(x.contiguous(), w1, b1, w2, b2, w3, b3, act, False)
+            reduced = x.view(bs, spp, hw, 128).float().mean(1)           # [bs, hw, 128]
+            unet = getattr(self, "propagation_{:02d}".format(step))
+            y = _unet_fast.autoencoder_forward_train(
+                unet, reduced.view(bs, h, w, 128).permute(0, 3, 1, 2))
+            prop = y.permute(0, 2, 3, 1).reshape(bs, hw, 128).to(th.bfloat16)
+        ctx = prop.unsqueeze(1).expand(bs, spp, hw, 128).reshape(npix, 128)
+        w1, b1, w2, b2, w3, b3, act, k2 = _chain_train.chain_weights(self.kernel_regressor, 256)
+        logits = _chain_train.ChainFn.apply(th.cat([x, ctx], 1).contiguous(), w1, b1, w2, b2, w3,
+                                            b3, act, True)               # fp32 [npix, k2 padded]
+        logits = logits.view(bs, spp, h, w, -1)
+        sum_r = sum_w = max_w = None
+        for sp in range(spp):
+            kernels = logits[:, sp, :, :, :k2].permute(0, 3, 1, 2).contiguous()
+            sum_r, sum_w, max_w = self.kernel_update(
+                crop_like(radiance[:, sp], kernels), kernels, sum_r, sum_w, max_w)
         output = sum_r / (sum_w + self.eps)
         crop = (self.ksize - 1) // 2
         return {"radiance": output[..., crop:-crop, crop:-crop]}

@@ -30,6 +30,7 @@ int main(void) {
       (entry_fn)sbmc_conv3x3_nhwc_bf16,
       (entry_fn)sbmc_b200_conv3x3_pair,
       (entry_fn)sbmc_maxpool2x2_nhwc_bf16,
+      (entry_fn)sbmc_linear_nhwc_bf16,
       (entry_fn)sbmc_upsample_concat_nhwc_bf16,
       (entry_fn)sbmc_bias_act_nhwc_bf16,
       (entry_fn)sbmc_nchw_to_nhwc_bf16,

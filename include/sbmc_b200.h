@@ -238,6 +238,73 @@ SBMC_API int sbmc_linear_nhwc_bf16(const void *x, const void *w, const float *bi
                                    int64_t pixels, int cin, int cout, int act, int out_f32,
                                    void *stream);
 
+/* General form of the layer above for the mixed-precision training pipeline
+ * (sbmc_b200/train_pipeline.py; reference: the train branch of sbmc/models.py:171-209):
+ *  - two sources: rows of x (bf16 [rows][cin_a], one row per SAMPLE, rows ordered image,
+ *    sample, pixel) are concatenated with rows of xb (bf16 [rows / spp][cin_b], one row per
+ *    PIXEL, shared by the spp samples of the pixel) -- the reference's
+ *    `th.cat([features, propagated.unsqueeze(1).repeat(...)], 2)` (models.py:175-177,193)
+ *    without materialising it; w is [cout][cin_a + cin_b]; needs hw % 256 == 0; cin_b = 0:
+ *    single source;
+ *  - mask != NULL (bf16 [rows][cout]): the result is multiplied by the derivative of
+ *    ReLU (mask_act 1) / LeakyReLU(0.01) (mask_act 2) read off the sign of mask -- the
+ *    data-gradient calls pass the saved activations of the previous layer;
+ *  - out_mode 0: bf16 rows, 1: fp32 rows, 2: fp32 channel planes
+ *    y[b * out_img_stride + s * out_smp_stride + c * hw + p] for c < cout_valid (the
+ *    kernel regressor's logits in the layout the splat reads, models.py:195-199). */
+SBMC_API int sbmc_linear2_nhwc_bf16(const void *x, int cin_a, const void *xb, int cin_b,
+                                    int64_t hw, int64_t spp, const void *w, const float *bias,
+                                    const void *mask, int mask_act, void *y, int out_mode,
+                                    int64_t out_img_stride, int64_t out_smp_stride,
+                                    int cout_valid, int64_t rows, int cout, int act,
+                                    void *stream);
+
+/* Weight and bias gradient of such a layer (csrc/wgrad.cu): dw[co][ci] (fp32, leading
+ * dimension ldw) = sum_r dy[r][co] x[r][ci] for co < cout_valid, ci < cin_valid, and
+ * db[co] = sum_r dy[r][co] (db may be NULL).  dy bf16 [rows][cout], x bf16 rows of
+ * x_row_pitch elements; cout, cin multiples of 128.  Split-K tcgen05 GEMM with MN-major
+ * operands: nsplit CTAs per 128 x 128 block, partial sums in `workspace`
+ * (nsplit * cout * (cin + 1) floats), reduced in a fixed order (deterministic).  The
+ * reference obtains these from cuDNN through autograd (sbmc/interfaces.py:78-106). */
+SBMC_API int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row_pitch,
+                                  int64_t rows, int cout, int cin, int nsplit,
+                                  float *workspace, float *dw, int64_t ldw, int cout_valid,
+                                  int cin_valid, float *db, void *stream);
+
+/* conv3x3 with the activation-derivative mask of sbmc_linear2_nhwc_bf16 in its epilogue
+ * (mask bf16 [n][h][w][cout] or NULL): the data-gradient convolutions of the U-net. */
+SBMC_API int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, const float *bias,
+                                           const void *mask, int mask_act, void *y, int64_t n,
+                                           int h, int w, int cin, int cout, int act,
+                                           void *stream);
+
+/* Memory-bound passes of the training pipeline on bf16 channels-innermost tensors
+ * (csrc/train_ops.cu).  in [n_img][spp][hw][c] -> out [n_img][hw][c] = scale * sum over the
+ * samples (bf16, or fp32 when out_f32 != 0): `features.mean(1)` (models.py:181). */
+SBMC_API int sbmc_spp_reduce_nhwc_bf16(const void *in, void *out, int out_f32, int64_t n_img,
+                                       int spp, int64_t hw, int c, float scale, void *stream);
+/* out[b][s][p][:] = a[b][s][p][:] + scale * r[b][p][:] (a may be NULL or equal out). */
+SBMC_API int sbmc_bcast_add_nhwc_bf16(const void *a, const void *r, void *out, int64_t n_img,
+                                      int spp, int64_t hw, int c, float scale, void *stream);
+/* Backward of MaxPool2d(2, 2) on x [n][h][w][c] (gradient to the first maximum of every
+ * window, as torch) + the skip-connection gradient dskip (rows of skip_pitch elements, may
+ * be NULL), times act'(x) (act as above, from the sign of x): modules.py:296-319. */
+SBMC_API int sbmc_maxpool2x2_bwd_nhwc_bf16(const void *x, const void *dpool, const void *dskip,
+                                           int64_t skip_pitch, void *out, int64_t n, int h,
+                                           int w, int c, int act, void *stream);
+/* Transpose of the decoder's bilinear upsampling (align_corners = False): dup rows of
+ * `pitch` elements [n][h][w] -> out [n][hl][wl][c], times act'(coarse) when act != 0. */
+SBMC_API int sbmc_upsample_bwd_nhwc_bf16(const void *dup, int64_t pitch, const void *coarse,
+                                         void *out, int64_t n, int hl, int wl, int h, int w,
+                                         int c, int act, void *stream);
+/* out = g * act'(y), elementwise on bf16 (elems multiple of 8). */
+SBMC_API int sbmc_dact_bf16(const void *y, const void *g, void *out, int64_t elems, int act,
+                            void *stream);
+/* out[c] = sum_r x[r][c] in fp32 (bias gradients); x bf16 rows of `pitch` elements;
+ * workspace: nblk * c floats; deterministic. */
+SBMC_API int sbmc_colsum_bf16(const void *x, int64_t pitch, int64_t rows, int c,
+                              float *workspace, int nblk, float *out, void *stream);
+
 /* 2 x 2 / stride 2 max pooling (the U-net's `downsample`, sbmc/modules.py:296-299:
  * nn.MaxPool2d(2, 2), floor mode) on bf16 channels-innermost x [n][h][w][c] ->
  * y [n][h/2][w/2][c]; c multiple of 8, 16-byte aligned pointers. */

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbmc_b200.so")
 
-_i64, _int, _ptr = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+_i64, _int, _ptr, _f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_float
 
 # name -> (restype, argtypes); mirrors include/sbmc_b200.h one to one.
 SIGNATURES = {
@@ -50,6 +50,22 @@ SIGNATURES = {
         (_int, [_ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_linear_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]),
+    "sbmc_linear2_nhwc_bf16":
+        (_int, [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _int, _i64,
+                _i64, _int, _i64, _int, _int, _ptr]),
+    "sbmc_wgrad_nhwc_bf16":
+        (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _int, _ptr, _ptr, _i64, _int, _int, _ptr,
+                _ptr]),
+    "sbmc_conv3x3_masked_nhwc_bf16":
+        (_int, [_ptr, _ptr, _ptr, _ptr, _int, _ptr, _i64, _int, _int, _int, _int, _int, _ptr]),
+    "sbmc_spp_reduce_nhwc_bf16": (_int, [_ptr, _ptr, _int, _i64, _int, _i64, _int, _f32, _ptr]),
+    "sbmc_bcast_add_nhwc_bf16": (_int, [_ptr, _ptr, _ptr, _i64, _int, _i64, _int, _f32, _ptr]),
+    "sbmc_maxpool2x2_bwd_nhwc_bf16":
+        (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _ptr]),
+    "sbmc_upsample_bwd_nhwc_bf16":
+        (_int, [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _int, _ptr]),
+    "sbmc_dact_bf16": (_int, [_ptr, _ptr, _ptr, _i64, _int, _ptr]),
+    "sbmc_colsum_bf16": (_int, [_ptr, _i64, _i64, _int, _ptr, _int, _ptr, _ptr]),
     "sbmc_maxpool2x2_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _int, _ptr]),
     "sbmc_bias_act_nhwc_bf16": (_int, [_ptr, _ptr, _i64, _int, _int, _ptr]),
     "sbmc_nchw_to_nhwc_bf16": (_int, [_ptr, _i64, _ptr, _i64, _i64, _int, _i64, _int, _ptr]),

@@ -58,6 +58,8 @@ __host__ __device__ constexpr int stages_for(int nt) { return nt == 128 ? 6 : 3;
 struct Args {
   const float *bias;
   __nv_bfloat16 *out;
+  const __nv_bfloat16 *mask;   // may be null: [n][H][W][Cout]; out *= act'(.) read off its sign
+  int mask_act;            // 1 ReLU, 2 LeakyReLU(0.01) (data-gradient calls of the training path)
   int act;                 // 0 none, 1 ReLU, 2 LeakyReLU(0.01)
   int H, W, Cin, Cout;
   int tiles_x, tiles_y, n_img, n_tiles_n;
@@ -243,6 +245,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
       __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + xq) * P.Cout + t.n0 +
                            (lane & 3) * 16;
       const float *bias = P.bias + t.n0;
+      const __nv_bfloat16 *mrow = nullptr;
+      if (P.mask && y < P.H && t.x0 + px < P.W)
+        mrow = P.mask + (((long long)t.n * P.H + y) * P.W + t.x0 + px) * P.Cout + t.n0;
+      const float mslope = (P.mask_act == 2) ? 0.01f : 0.f;
 #pragma unroll 1
       for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 64) {
         const uint32_t col = (NT == 128) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
@@ -251,6 +257,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
         for (int hh = 0; hh < 2; ++hh) {
           float v[32];
           tmem_ld_32x32b_x32(lane_base + col + 32 * hh, v);
+          if (mrow) apply_act_mask32(v, mrow + c0 + 32 * hh, mslope);
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 32 * hh + 4 * q4));
@@ -503,6 +510,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Ci
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
         tmem_ld_32x32b_x32(lane_base + buf * 256 + g * 128 + c0 + 32 * hh, v);
+        if (P.mask && valid)
+          apply_act_mask32(v, P.mask + (own - P.out) + c0 + 32 * hh, (P.mask_act == 2) ? 0.01f : 0.f);
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 b = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + 32 * hh + 4 * q4));
@@ -579,11 +588,24 @@ extern "C" int sbmc_b200_conv3x3_pair(int flag) {
   return prev;
 }
 
+extern "C" int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, const float *bias,
+                                             const void *mask, int mask_act, void *y, int64_t n,
+                                             int h, int w, int cin, int cout, int act,
+                                             void *stream);
+
 extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *bias, void *y,
                                       int64_t n, int h, int w, int cin, int cout, int act,
                                       void *stream) {
+  return sbmc_conv3x3_masked_nhwc_bf16(x, w9, bias, nullptr, 0, y, n, h, w, cin, cout, act, stream);
+}
+
+extern "C" int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, const float *bias,
+                                             const void *mask, int mask_act, void *y, int64_t n,
+                                             int h, int w, int cin, int cout, int act,
+                                             void *stream) {
   using namespace sbmc;
-  if (n < 0 || h < 1 || w < 1 || cin < 1 || cout < 1 || act < 0 || act > 2) {
+  if (n < 0 || h < 1 || w < 1 || cin < 1 || cout < 1 || act < 0 || act > 2 ||
+      (mask && (mask_act < 1 || mask_act > 2))) {
     set_error("conv3x3: invalid shape");
     return SBMC_EINVAL;
   }
@@ -597,13 +619,14 @@ extern "C" int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float
     return SBMC_EUNSUPPORTED;
   }
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
-       reinterpret_cast<uintptr_t>(w9)) & 15) {
+       reinterpret_cast<uintptr_t>(w9) | reinterpret_cast<uintptr_t>(mask)) & 15) {
     set_error("conv3x3: pointers must be 16-byte aligned");
     return SBMC_EALIGN;
   }
   const int nt = (cout % 256 == 0) ? 256 : 128;
   c3::Args a;
   a.bias = bias; a.out = static_cast<__nv_bfloat16 *>(y); a.act = act;
+  a.mask = static_cast<const __nv_bfloat16 *>(mask); a.mask_act = mask_act;
   a.H = h; a.W = w; a.Cin = cin; a.Cout = cout;
   a.tiles_x = (w + c3::kSegPx - 1) / c3::kSegPx;
   a.tiles_y = (h + c3::kRows - 1) / c3::kRows;

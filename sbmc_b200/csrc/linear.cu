@@ -31,10 +31,16 @@ __host__ __device__ constexpr int b_stages(int nt) { return nt == 128 ? 6 : 3; }
 struct Args {
   const float *bias;       // may be null
   void *out;
+  const __nv_bfloat16 *mask;   // may be null: [rows][Cout], out *= act'(mask) (mask_act)
   int act;                 // 0 none, 1 ReLU, 2 LeakyReLU(0.01)
-  int out_f32;
-  long long P;             // pixels (rows)
-  int Cin, Cout;
+  int mask_act;            // derivative selected by the sign of mask: 1 ReLU, 2 LeakyReLU
+  int out_mode;            // 0 bf16 rows, 1 fp32 rows, 2 fp32 channel planes
+  long long P;             // rows
+  int Cin, Cout;           // Cin = CinA + CinB
+  int slabs_a;             // 64-channel slabs that come from the first source
+  long long hw, spp;       // row r = (image b, sample s, pixel p), r = (b spp + s) hw + p
+  long long out_img_stride, out_smp_stride;   // plane mode: elements between images / samples
+  int cout_valid;          // plane mode: channels >= cout_valid are not stored
   long long tiles_p;
   long long ntiles;
 };
@@ -51,7 +57,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
-linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {Cin, P}
+linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {CinA, P}
+              const __grid_constant__ CUtensorMap amap2,     // xb {CinB, pixels} (or = amap)
               const __grid_constant__ CUtensorMap wmap,      // w {Cin, Cout}
               const Args P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -81,10 +88,16 @@ linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {Cin, P}
       int ab = 0;
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const long long p0 = (tile % P.tiles_p) * kTilePx;
+        // second source: one row per PIXEL, shared by the samples of the pixel
+        // (hw % 256 == 0 is checked by the host, so a tile never straddles two samples)
+        const long long q0 = (P.slabs_a < nslabs) ? (p0 / (P.spp * P.hw)) * P.hw + p0 % P.hw : 0;
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + B_AE + ab, ((ph >> ab) & 1) ^ 1); ph ^= 1u << ab;
           mbar_expect_tx(bars + B_AF + ab, (uint32_t)kASlab);
-          tma_load_2d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, (int)p0);
+          if (s < P.slabs_a)
+            tma_load_2d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, (int)p0);
+          else
+            tma_load_2d(sA + ab * kASlab, &amap2, bars + B_AF + ab, (s - P.slabs_a) * 64, (int)q0);
           ab = (ab + 1 == kAStages) ? 0 : ab + 1;
         }
       }
@@ -149,6 +162,12 @@ linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {Cin, P}
       mbar_wait(bars + B_ACCF + buf, (ph >> buf) & 1); ph ^= 1u << buf;
       tcgen05_fence_after();
       const bool valid = p < P.P;
+      float *plane0 = nullptr;
+      if (P.out_mode == 2 && valid) {
+        const long long img = p / P.hw;
+        plane0 = static_cast<float *>(P.out) + (img / P.spp) * P.out_img_stride +
+                 (img % P.spp) * P.out_smp_stride + (p - img * P.hw);
+      }
 #pragma unroll 1
       for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 32) {
         const uint32_t col = (NT == 128) ? buf * 256 + g * 128 + c0 : g * 256 + c0;
@@ -168,8 +187,14 @@ linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {Cin, P}
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
         }
+        if (P.mask && valid)
+          apply_act_mask32(v, P.mask + p * P.Cout + n0 + c0, (P.mask_act == 2) ? 0.01f : 0.f);
         if (valid) {
-          if (P.out_f32) {
+          if (P.out_mode == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < P.cout_valid) plane0[(long long)(n0 + c0 + i) * P.hw] = v[i];
+          } else if (P.out_mode == 1) {
             float *dst = static_cast<float *>(P.out) + p * P.Cout + n0 + c0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) stg256(dst + 8 * k, reinterpret_cast<const uint32_t *>(v) + 8 * k);
@@ -194,15 +219,20 @@ linear_kernel(const __grid_constant__ CUtensorMap amap,      // x {Cin, P}
 }
 
 template <int NT>
-static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, cudaStream_t st) {
+static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &am2,
+                  const CUtensorMap &wm, cudaStream_t st) {
   const size_t smem = (size_t)kAStages * kASlab + (size_t)b_stages(NT) * NT * 128 +
                       B_COUNT * sizeof(uint64_t) + 16;
   auto kern = linear_kernel<NT>;
-  SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool configured = false;     // once: the call is not a stream operation
+  if (!configured) {
+    SBMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
   const long long grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   {
     KernelTimer timer(SBMC_KERNEL_CONV1X1, st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(am, wm, a);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(am, am2, wm, a);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
@@ -212,39 +242,73 @@ static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, c
 }  // namespace lin
 }  // namespace sbmc
 
-extern "C" int sbmc_linear_nhwc_bf16(const void *x, const void *w, const float *bias, void *y,
-                                     int64_t pixels, int cin, int cout, int act, int out_f32,
-                                     void *stream) {
+extern "C" int sbmc_linear2_nhwc_bf16(const void *x, int cin_a, const void *xb, int cin_b,
+                                      int64_t hw, int64_t spp, const void *w,
+                                      const float *bias, const void *mask, int mask_act,
+                                      void *y, int out_mode, int64_t out_img_stride,
+                                      int64_t out_smp_stride, int cout_valid, int64_t rows,
+                                      int cout, int act, void *stream) {
   using namespace sbmc;
-  if (pixels < 0 || cin < 1 || cout < 1 || act < 0 || act > 2) {
-    set_error("linear: invalid shape");
+  if (rows < 0 || cin_a < 1 || cin_b < 0 || cout < 1 || act < 0 || act > 2 || out_mode < 0 ||
+      out_mode > 2 || (mask && (mask_act < 1 || mask_act > 2))) {
+    set_error("linear: invalid argument");
     return SBMC_EINVAL;
   }
-  if (pixels == 0) return SBMC_OK;
-  if (!x || !w || !y) {
+  if (rows == 0) return SBMC_OK;
+  if (!x || !w || !y || (cin_b > 0 && !xb)) {
     set_error("linear: null pointer argument");
     return SBMC_EINVAL;
   }
-  if (cin % 64 != 0 || cout % 128 != 0 || pixels >= (1ll << 31)) {
-    set_error("linear: needs cin %% 64 == 0 and cout %% 128 == 0 (got %d, %d)", cin, cout);
+  if (cin_a % 64 != 0 || cin_b % 64 != 0 || cout % 128 != 0 || rows >= (1ll << 31)) {
+    set_error("linear: needs cin %% 64 == 0 and cout %% 128 == 0 (got %d + %d, %d)", cin_a,
+              cin_b, cout);
+    return SBMC_EUNSUPPORTED;
+  }
+  if ((cin_b > 0 || out_mode == 2) && (hw < 1 || spp < 1 || rows % hw != 0)) {
+    set_error("linear: rows must be images x samples x hw pixels");
+    return SBMC_EINVAL;
+  }
+  if (cin_b > 0 && hw % lin::kTilePx != 0) {
+    set_error("linear: the two-source form needs hw %% %d == 0 (got %lld)", lin::kTilePx,
+              (long long)hw);
+    return SBMC_EUNSUPPORTED;
+  }
+  if (mask && out_mode == 2) {
+    set_error("linear: no mask in plane mode");
     return SBMC_EUNSUPPORTED;
   }
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
-       reinterpret_cast<uintptr_t>(w)) & 31) {
+       reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(xb) |
+       reinterpret_cast<uintptr_t>(mask)) & 31) {
     set_error("linear: pointers must be 32-byte aligned");
     return SBMC_EALIGN;
   }
   const int nt = (cout % 256 == 0) ? 256 : 128;
   lin::Args a;
-  a.bias = bias; a.out = y; a.act = act; a.out_f32 = out_f32 ? 1 : 0;
-  a.P = pixels; a.Cin = cin; a.Cout = cout;
-  a.tiles_p = (pixels + lin::kTilePx - 1) / lin::kTilePx;
+  a.bias = bias; a.out = y; a.act = act; a.out_mode = out_mode;
+  a.mask = static_cast<const __nv_bfloat16 *>(mask); a.mask_act = mask_act;
+  a.P = rows; a.Cin = cin_a + cin_b; a.Cout = cout; a.slabs_a = cin_a / 64;
+  a.hw = hw > 0 ? hw : 1; a.spp = spp > 0 ? spp : 1;
+  a.out_img_stride = out_img_stride; a.out_smp_stride = out_smp_stride;
+  a.cout_valid = cout_valid > 0 ? cout_valid : cout;
+  a.tiles_p = (rows + lin::kTilePx - 1) / lin::kTilePx;
   a.ntiles = a.tiles_p * (cout / nt);
-  CUtensorMap am, wm;
-  if (!encode_tensor_map_bf16_2d_sw128(&am, x, (uint64_t)cin, (uint64_t)pixels, 64, lin::kTilePx) ||
-      !encode_tensor_map_bf16_2d_sw128(&wm, w, (uint64_t)cin, (uint64_t)cout, 64, (uint32_t)nt))
+  CUtensorMap am, am2, wm;
+  if (!encode_tensor_map_bf16_2d_sw128(&am, x, (uint64_t)cin_a, (uint64_t)rows, 64, lin::kTilePx) ||
+      !encode_tensor_map_bf16_2d_sw128(&wm, w, (uint64_t)a.Cin, (uint64_t)cout, 64, (uint32_t)nt))
+    return SBMC_ECUDA;
+  am2 = am;
+  if (cin_b > 0 && !encode_tensor_map_bf16_2d_sw128(&am2, xb, (uint64_t)cin_b,
+                                                    (uint64_t)(rows / spp), 64, lin::kTilePx))
     return SBMC_ECUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   note_path(1);
-  return nt == 256 ? lin::launch<256>(a, am, wm, st) : lin::launch<128>(a, am, wm, st);
+  return nt == 256 ? lin::launch<256>(a, am, am2, wm, st) : lin::launch<128>(a, am, am2, wm, st);
+}
+
+extern "C" int sbmc_linear_nhwc_bf16(const void *x, const void *w, const float *bias, void *y,
+                                     int64_t pixels, int cin, int cout, int act, int out_f32,
+                                     void *stream) {
+  return sbmc_linear2_nhwc_bf16(x, cin, nullptr, 0, 0, 0, w, bias, nullptr, 0, y,
+                                out_f32 ? 1 : 0, 0, 0, 0, pixels, cout, act, stream);
 }

@@ -179,5 +179,25 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t *v) {
                : "memory");
 }
 
+// Backward of ReLU / LeakyReLU(0.01) fused into an epilogue: v[i] *= act'(pre-activation),
+// read off the sign of the saved OUTPUT m[i] of that activation (bf16, 32 consecutive
+// channels of this thread's row, 16-byte aligned): m > 0 <=> pre-activation > 0, and the
+// derivative at 0 is `slope` (0 for ReLU) like torch's.
+__device__ __forceinline__ void apply_act_mask32(float (&v)[32], const void *m, float slope) {
+  const uint4 *mp = reinterpret_cast<const uint4 *>(m);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const uint4 mm = __ldg(mp + q4);
+    const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = w4[j] & 0xFFFFu, hi = w4[j] >> 16;
+      // bf16 > 0: sign bit clear and not zero
+      if (!(lo != 0 && lo < 0x8000u)) v[8 * q4 + 2 * j] *= slope;
+      if (!(hi != 0 && hi < 0x8000u)) v[8 * q4 + 2 * j + 1] *= slope;
+    }
+  }
+}
+
 #endif  // __CUDACC__
 }  // namespace sbmc

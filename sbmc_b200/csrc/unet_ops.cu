@@ -307,12 +307,12 @@ extern "C" int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void
   const i64 tiles = n * ((hw + kT2Px - 1) / kT2Px);
   i64 blocks = tiles < (i64)num_sms() * 8 ? tiles : (i64)num_sms() * 8;
   const size_t smem = (size_t)kT2Px * (cpad / 2 + 1) * sizeof(uint32_t);
-  if (smem > 96 * 1024) {
+  if (smem > 200 * 1024) {
     set_error("nchw_to_nhwc: cpad %d too large", cpad);
     return SBMC_EUNSUPPORTED;
   }
   SBMC_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_bf16_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_OTHER, st);

@@ -27,6 +27,7 @@ import torch as th
 import torch.nn as nn
 
 from . import chain_train as _chain_train
+from . import train_pipeline as _train_pipeline
 from . import conv1x1 as _conv1x1
 from . import unet_fast as _unet_fast
 from . import modules as ops
@@ -136,6 +137,9 @@ class Multisteps(nn.Module):
                 and th.is_grad_enabled() and self._nhwc_pipeline_ok(nf)
                 and all(_unet_fast.supports_training(getattr(self, "propagation_{:02d}".format(i)))
                         for i in range(self.nsteps))):
+            if _train_pipeline.supported(self, nf, gfeatures.shape[1], h, w):
+                # few autograd nodes, every forward / backward pass a repo kernel
+                return _train_pipeline.forward_train(self, radiance, features, gfeatures)
             return self._forward_train_nhwc(radiance, features, gfeatures)
 
         propagated = None

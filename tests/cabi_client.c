@@ -31,6 +31,15 @@ int main(void) {
       (entry_fn)sbmc_b200_conv3x3_pair,
       (entry_fn)sbmc_maxpool2x2_nhwc_bf16,
       (entry_fn)sbmc_linear_nhwc_bf16,
+      (entry_fn)sbmc_linear2_nhwc_bf16,
+      (entry_fn)sbmc_wgrad_nhwc_bf16,
+      (entry_fn)sbmc_conv3x3_masked_nhwc_bf16,
+      (entry_fn)sbmc_spp_reduce_nhwc_bf16,
+      (entry_fn)sbmc_bcast_add_nhwc_bf16,
+      (entry_fn)sbmc_maxpool2x2_bwd_nhwc_bf16,
+      (entry_fn)sbmc_upsample_bwd_nhwc_bf16,
+      (entry_fn)sbmc_dact_bf16,
+      (entry_fn)sbmc_colsum_bf16,
       (entry_fn)sbmc_upsample_concat_nhwc_bf16,
       (entry_fn)sbmc_bias_act_nhwc_bf16,
       (entry_fn)sbmc_nchw_to_nhwc_bf16,

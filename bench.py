@@ -512,24 +512,30 @@ def run_secondary(a, th, dist, dev, rank, world):
             sec["config4_train_step"] = {
                 "workload": "Multisteps(93,3) train step, B=8, spp=8, 128x128, K=21, "
                             "fwd + TonemappedRelativeMSE + bwd + clip + Adam, 1 GPU",
-                "path": "cuDNN convs (variants bf16_unet_*: the U-net's forward and data-gradient "
-                        "convolutions on the repo's tcgen05 kernel); fused splat forward / "
-                        "backward and fused clip+Adam are repo kernels"}
-            for label, tf32, own in (("fp32_strict", False, 0),
-                                     ("tf32_convs_allowed", True, 0),
-                                     ("bf16_unet_own_kernels_rest_fp32_strict", False, 1),
-                                     ("bf16_unet_own_kernels_rest_tf32", True, 1),
-                                     ("bf16_train_chains_and_unet_own_kernels", False, 2)):
+                "path": "fp32_strict / tf32_convs_allowed: the reference's op chain (cuDNN "
+                        "convolutions) with the repo's fused splat forward / backward and fused "
+                        "clip+Adam; bf16_unet_*: U-net forward and data-gradient convolutions on "
+                        "the repo's tcgen05 kernel; bf16_train_pipeline*: sbmc_b200/"
+                        "train_pipeline.py -- every GEMM-shaped pass except the 3x3 weight "
+                        "gradients on repo tcgen05 kernels"}
+            for label, tf32, own, graph in (
+                    ("fp32_strict", False, 0, False),
+                    ("tf32_convs_allowed", True, 0, False),
+                    ("tf32_convs_allowed_cuda_graph", True, 0, True),
+                    ("bf16_unet_own_kernels_rest_fp32_strict", False, 1, False),
+                    ("bf16_unet_own_kernels_rest_tf32", True, 1, False),
+                    ("bf16_train_pipeline", False, 2, False),
+                    ("bf16_train_pipeline_cuda_graph", False, 2, True)):
                 th.manual_seed(0)
                 net = models.Multisteps(93, 3).to(dev).train()
                 net.bf16_unet_train = own == 1
                 net.bf16_train = own == 2
                 iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True,
                                                                 fused_optimizer=True,
-                                                                allow_tf32=tf32)
+                                                                allow_tf32=tf32, cuda_graph=graph)
 
                 def train():
-                    return iface.backward(batch, iface.forward(batch))
+                    return iface.train_step(batch)
                 ms = _timed_cuda(th, train, 2, 4)
                 sec["config4_train_step"][label] = {
                     "ms": ms, "Msamples_per_s": 8 * 8 * 128 * 128 / ms / 1e3,
@@ -539,8 +545,9 @@ def run_secondary(a, th, dist, dev, rank, world):
                        "convolutions on csrc/conv3x3.cu, weight gradients on cuDNN bf16"
                        if own else "")
                     + ("; 1x1 chains in bf16: forward and data-gradient layers on "
-                       "csrc/linear.cu, weight gradients on cuBLAS bf16; no fp32 "
-                       "convolution left" if own == 2 else "")}
+                       "csrc/linear.cu, weight / bias gradients on csrc/wgrad.cu; 3x3 weight "
+                       "gradients on cuDNN bf16; no fp32 convolution left" if own == 2 else "")
+                    + ("; whole step replayed from one CUDA graph" if graph else "")}
                 del net, iface
             th.backends.cudnn.allow_tf32 = False
             th.backends.cuda.matmul.allow_tf32 = False

@@ -415,6 +415,14 @@ SBMC_API int sbmc_multi_tensor_adam_f32(const int64_t *tensors, const int64_t *c
                                         double bias_correction1, double bias_correction2_sqrt,
                                         void *stream);
 
+/* The same update for CUDA-graph capture: the step count is a device float (*step = steps
+ * taken so far; incremented by one after the update), so a replayed graph advances the
+ * bias corrections.  Used by FusedAdam(capturable=True). */
+SBMC_API int sbmc_multi_tensor_adam_devstep_f32(const int64_t *tensors, const int64_t *chunks,
+                                                int64_t nchunks, const float *clip_coef,
+                                                double lr, double beta1, double beta2,
+                                                double eps, float *step, void *stream);
+
 /* ---- row-band entry points (H-sharding across GPUs, host streaming) ------ *
  * A band is `h` consecutive image rows.  weights / output / sum_w / d_output /
  * d_sum_w / d_weights cover exactly the band.  `data_ext` ([n][c][halo_top +

@@ -139,8 +139,12 @@ class Trainer(object):
             while num_epochs is None or epoch < num_epochs:
                 self._emit("epoch_start", epoch)
                 for batch in dataloader:
-                    fwd = self.interface.forward(batch)
-                    bwd = self.interface.backward(batch, fwd)
+                    step = getattr(self.interface, "train_step", None)
+                    if step is not None:        # forward + backward in one call (CUDA graphs)
+                        fwd, bwd = step(batch)
+                    else:
+                        fwd = self.interface.forward(batch)
+                        bwd = self.interface.backward(batch, fwd)
                     self._emit("batch_end", batch, fwd, bwd)
                     steps += 1
                     if max_steps is not None and steps >= max_steps:

@@ -77,6 +77,8 @@ SIGNATURES = {
         (_int, [_ptr, _ptr, _i64, _ptr, ctypes.c_float, _ptr, _ptr]),
     "sbmc_multi_tensor_adam_f32":
         (_int, [_ptr, _ptr, _i64, _ptr] + [ctypes.c_double] * 6 + [_ptr]),
+    "sbmc_multi_tensor_adam_devstep_f32":
+        (_int, [_ptr, _ptr, _i64, _ptr] + [ctypes.c_double] * 4 + [_ptr, _ptr]),
     "sbmc_kernel_weighting_fwd_band_f32":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _i64, _i64, _int, _int, _int,
                 _int, _ptr]),

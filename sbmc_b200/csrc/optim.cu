@@ -71,9 +71,56 @@ __global__ void __launch_bounds__(256) multi_adam_kernel(const long long *__rest
     adam_element(t.p + i, t.g + i, t.m + i, t.v + i, coef, s);
 }
 
+// Capturable variant (CUDA graphs): the step count lives on the device, so that a replayed
+// graph advances the bias corrections; they are derived in double per thread, as the host
+// does for the plain entry point.  *step = steps taken so far.
+__global__ void __launch_bounds__(256) multi_adam_devstep_kernel(
+    const long long *__restrict__ tensors, const long long *__restrict__ chunks,
+    const float *__restrict__ coef_ptr, double lr, double beta1, double beta2, double eps,
+    const float *__restrict__ step) {
+  const double t = (double)(*step) + 1.0;
+  const AdamScalars s = adam_scalars(lr, beta1, beta2, eps, 1.0 - pow(beta1, t),
+                                     sqrt(1.0 - pow(beta2, t)));
+  const long long c = blockIdx.x;
+  const MtTensor tn = mt_tensor(tensors, chunks[2 * c]);
+  const long long start = chunks[2 * c + 1];
+  const long long stop = (start + SBMC_MT_CHUNK_ELEMS < tn.n) ? start + SBMC_MT_CHUNK_ELEMS : tn.n;
+  const float coef = coef_ptr ? *coef_ptr : 1.0f;
+  for (long long i = start + threadIdx.x; i < stop; i += 256)
+    adam_element(tn.p + i, tn.g + i, tn.m + i, tn.v + i, coef, s);
+}
+__global__ void step_increment_kernel(float *step) { *step += 1.0f; }
+
 }  // namespace sbmc
 
 extern "C" {
+
+int sbmc_multi_tensor_adam_devstep_f32(const int64_t *tensors, const int64_t *chunks,
+                                       int64_t nchunks, const float *clip_coef, double lr,
+                                       double beta1, double beta2, double eps, float *step,
+                                       void *stream) {
+  if (nchunks < 0 || nchunks > 0x7FFFFFFF) {
+    sbmc::set_error("adam: invalid chunk count %lld", (long long)nchunks);
+    return SBMC_EINVAL;
+  }
+  if (!step || (nchunks > 0 && (!tensors || !chunks))) {
+    sbmc::set_error("adam: null pointer argument");
+    return SBMC_EINVAL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    sbmc::KernelTimer timer(SBMC_KERNEL_OPTIM, st);
+    if (nchunks > 0)
+      sbmc::multi_adam_devstep_kernel<<<(unsigned)nchunks, 256, 0, st>>>(
+          reinterpret_cast<const long long *>(tensors),
+          reinterpret_cast<const long long *>(chunks), clip_coef, lr, beta1, beta2, eps, step);
+    sbmc::step_increment_kernel<<<1, 1, 0, st>>>(step);
+  }
+  SBMC_CUDA_OK(cudaGetLastError());
+  sbmc::count_launch(2);
+  sbmc::note_path(1);
+  return SBMC_OK;
+}
 
 int sbmc_multi_tensor_grad_norm_f32(const int64_t *tensors, const int64_t *chunks,
                                     int64_t nchunks, float *partial, float max_norm,

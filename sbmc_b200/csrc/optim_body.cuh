@@ -46,7 +46,7 @@ struct AdamScalars {
   float bc2_sqrt;             // sqrt(1 - beta2^t)
 };
 
-static inline AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps,
+SBMC_OPT_HD AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps,
                                        double bias_correction1, double bias_correction2_sqrt) {
   AdamScalars s;
   s.lr_over_bc1 = (float)(lr / bias_correction1);

@@ -232,12 +232,28 @@ colsum_partial_kernel(const uint4 *__restrict__ x, i64 pitch8, i64 rows, int c8,
     partial[(i64)blockIdx.x * c8 * 8 + i] = s;
   }
 }
+// 32 consecutive channels x 8 warps; warp w adds partials w, w + 8, ...
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float *__restrict__ partial, int nblk, int c, float *__restrict__ out) {
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < c; i += gridDim.x * 256) {
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[(i64)b * c + i];
-    out[i] = s;
+  __shared__ float red[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < c) {
+    int b = warp;
+    for (; b + 8 < nblk; b += 16) {
+      a0 += partial[(i64)b * c + i];
+      a1 += partial[(i64)(b + 8) * c + i];
+    }
+    for (; b < nblk; b += 8) a0 += partial[(i64)b * c + i];
+  }
+  red[warp][lane] = a0 + a1;
+  __syncthreads();
+  if (warp == 0 && i < c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += red[w][lane];
+    out[i] = acc;
   }
 }
 
@@ -410,7 +426,7 @@ extern "C" int sbmc_colsum_bf16(const void *x, int64_t pitch, int64_t rows, int 
     KernelTimer timer(SBMC_KERNEL_OTHER, st);
     tr::colsum_partial_kernel<<<(unsigned)nblk, 256, (size_t)lanes * c * sizeof(float), st>>>(
         static_cast<const uint4 *>(x), pitch / 8, rows, c8, workspace);
-    tr::colsum_final_kernel<<<(c + 255) / 256, 256, 0, st>>>(workspace, nblk, c, out);
+    tr::colsum_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(workspace, nblk, c, out);
   }
   count_launch(2);
   SBMC_CUDA_OK(cudaGetLastError());

@@ -168,25 +168,49 @@ wgrad_kernel(const __grid_constant__ CUtensorMap ymap,      // dY {Cout, rows}
 }
 
 // dw[co][ci] (leading dimension ldw) = sum over the splits, co < cout_valid, ci < cin_valid.
+// Block = 32 consecutive outputs x 8 warps; warp w adds splits w, w + 8, ... (independent
+// coalesced 128-byte loads), the eight partial sums are added in a fixed order.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ partial_b,
                     int nsplit, int Cout, int Cin, float *__restrict__ dw, long long ldw,
                     int cout_valid, int cin_valid, float *__restrict__ db) {
+  __shared__ float red[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)cout_valid * cin_valid;
+  const long long nb = (total + 31) / 32;                 // blocks of weight outputs
   const long long stride = (long long)Cout * Cin;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int co = (int)(i / cin_valid), ci = (int)(i % cin_valid);
-    const float *p = partial + (long long)co * Cin + ci;
-    float acc = 0.f;
-    for (int s = 0; s < nsplit; ++s) acc += p[s * stride];
-    dw[co * ldw + ci] = acc;
-  }
-  if (db && blockIdx.x == 0) {
-    for (int co = threadIdx.x; co < cout_valid; co += 256) {
-      float acc = 0.f;
-      for (int s = 0; s < nsplit; ++s) acc += partial_b[(long long)s * Cout + co];
-      db[co] = acc;
+  for (long long blk = blockIdx.x; blk < nb + (db ? (cout_valid + 31) / 32 : 0); blk += gridDim.x) {
+    const bool bias = blk >= nb;
+    const long long i = (bias ? blk - nb : blk) * 32 + lane;
+    const bool ok = i < (bias ? (long long)cout_valid : total);
+    int co = 0, ci = 0;
+    const float *p = partial_b;
+    long long st = Cout;
+    if (!bias) {
+      co = (int)(i / cin_valid); ci = (int)(i - (long long)co * cin_valid);
+      p = partial + (long long)co * Cin + ci;
+      st = stride;
+    } else {
+      p = partial_b + i;
     }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (ok) {
+      int s = warp;
+      for (; s + 24 < nsplit; s += 32) {
+        a0 += p[s * st]; a1 += p[(s + 8) * st]; a2 += p[(s + 16) * st]; a3 += p[(s + 24) * st];
+      }
+      for (; s < nsplit; s += 8) a0 += p[s * st];
+    }
+    red[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && ok) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += red[w][lane];
+      if (bias) db[i] = acc;
+      else dw[co * ldw + ci] = acc;
+    }
+    __syncthreads();
   }
 }
 
@@ -246,7 +270,8 @@ extern "C" int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
   const long long total = (long long)cout_valid * cin_valid;
-  const unsigned blocks = (unsigned)(total / 256 < 1 ? 1 : (total / 256 > 1184 ? 1184 : total / 256));
+  const long long rblocks = (total + 31) / 32 + (db ? (cout_valid + 31) / 32 : 0);
+  const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
   wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a.partial, a.partial_b, nsplit, cout, cin, dw, ldw,
                                                   cout_valid, cin_valid, db);
   count_launch();

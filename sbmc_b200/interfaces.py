@@ -18,6 +18,79 @@ LOG = get_logger(__name__)
 _GRAD_CLIP = 1000
 
 
+class _GraphedStep(object):
+    """One training step of `SampleBasedDenoiserInterface` on static buffers, captured in a
+    CUDA graph.  Gradients are static too (allocated once, zeroed inside the graph), so
+    the fused optimizer's device tables never change.  The two eager warm-up steps that
+    PyTorch's capture protocol asks for run on the first batch and are undone (parameters
+    and optimizer state restored) before the capture."""
+
+    def __init__(self, iface, batch):
+        self.iface = iface
+        self.static = {k: (v.detach().clone() if isinstance(v, th.Tensor) else v)
+                       for k, v in batch.items()}
+        self.params = [p for p in iface.model.parameters() if p.requires_grad]
+        for p in self.params:
+            if p.grad is None:
+                p.grad = th.zeros_like(p, memory_format=th.contiguous_format)
+        opt = iface.optimizer
+        saved_p = [p.detach().clone() for p in self.params]
+        saved_s = {p: {k: (v.clone() if isinstance(v, th.Tensor) else v)
+                       for k, v in opt.state[p].items()}
+                   for p in self.params if opt.state.get(p)}
+        side = th.cuda.Stream()
+        side.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(side):
+            for _ in range(2):
+                self._body()
+        th.cuda.current_stream().wait_stream(side)
+        th.cuda.synchronize()
+        with th.no_grad():
+            for p, q in zip(self.params, saved_p):
+                p.copy_(q)
+                for k, v in opt.state[p].items():
+                    if isinstance(v, th.Tensor):
+                        old = saved_s.get(p, {}).get(k)
+                        v.zero_() if old is None else v.copy_(old)
+        del saved_p, saved_s
+        self.graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(self.graph):
+            self._body()
+        LOG.info("training step captured in a CUDA graph (%s)",
+                 ", ".join("%s %s" % (k, tuple(v.shape)) for k, v in self.static.items()
+                           if isinstance(v, th.Tensor)))
+
+    def _body(self):
+        iface = self.iface
+        th._foreach_zero_([p.grad for p in self.params])
+        fwd = iface.model(self.static)
+        loss, out, tgt = iface._scores(self.static, fwd)
+        loss.backward()
+        iface.optimizer.step(max_norm=_GRAD_CLIP)
+        with th.no_grad():
+            self.scalars = th.stack([loss.detach().float().reshape(()),
+                                     iface.rmse_fn(out, tgt).float().reshape(()),
+                                     iface.optimizer.last_grad_norm[0].reshape(())])
+            self.out = out.detach()
+
+    def run(self, batch):
+        for k, v in batch.items():
+            if isinstance(v, th.Tensor):
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        from .optim import _bump_version
+        for p in self.params:               # the replay wrote the parameters behind autograd's back
+            _bump_version(p)
+        value, rmse, norm = self.scalars.tolist()
+        if not math.isfinite(value):
+            kind = "NaN" if math.isnan(value) else "Infinite"
+            LOG.error("%s loss, there might be outliers in the data.", kind)
+            raise RuntimeError("%s loss at train time." % kind)
+        if norm > _GRAD_CLIP:
+            LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, norm)
+        return {"radiance": self.out}, {"loss": value, "rmse": rmse}
+
+
 class SampleBasedDenoiserInterface(object):
     """model: nn.Module taking / returning dicts; lr: Adam step size; cuda: move
     the model (and every batch) to the GPU; fused_optimizer: see below;
@@ -26,7 +99,8 @@ class SampleBasedDenoiserInterface(object):
     switched OFF unless asked for -- the policy is set here, explicitly, and
     logged."""
 
-    def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False, allow_tf32=False):
+    def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False, allow_tf32=False,
+                 cuda_graph=False):
         self.allow_tf32 = bool(allow_tf32)
         th.backends.cudnn.allow_tf32 = self.allow_tf32
         th.backends.cuda.matmul.allow_tf32 = self.allow_tf32
@@ -37,10 +111,18 @@ class SampleBasedDenoiserInterface(object):
         self.rmse_fn = losses.RelativeMSE()
         # fused_optimizer (extra, CUDA only): clipping + Adam over all parameter
         # tensors in three launches (sbmc_b200.optim.FusedAdam)
+        # cuda_graph (extra, CUDA only): `train_step` captures forward + loss + backward +
+        # clip + Adam of one batch shape in a CUDA graph and replays it (the step is a few
+        # hundred small launches: without the graph the host, not the GPU, sets its pace)
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        if self.cuda_graph and not (cuda and fused_optimizer):
+            raise ValueError("cuda_graph needs cuda=True and fused_optimizer=True")
         self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:
             from .optim import FusedAdam
-            self.optimizer = FusedAdam(self.model.parameters(), lr=lr)
+            self.optimizer = FusedAdam(self.model.parameters(), lr=lr,
+                                       capturable=self.cuda_graph)
         else:
             self.optimizer = th.optim.Adam(self.model.parameters(), lr=lr)
 
@@ -86,6 +168,22 @@ class SampleBasedDenoiserInterface(object):
         if norm > _GRAD_CLIP:
             LOG.info("Clipped gradients %s -> %s", _GRAD_CLIP, norm)
         return {"loss": value, "rmse": rmse}
+
+    def train_step(self, batch):
+        """forward + backward in one call -> (fwd, bwd) as `forward` / `backward` return
+        them.  With cuda_graph the whole step is one graph replay per batch signature."""
+        if not self.cuda_graph:
+            fwd = self.forward(batch)
+            return fwd, self.backward(batch, fwd)
+        batch = self._to_device(batch)
+        key = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in batch.items()
+                           if isinstance(v, th.Tensor)))
+        step = self._graphs.get(key)
+        if step is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            step = self._graphs[key] = _GraphedStep(self, batch)
+        return step.run(batch)
 
     def init_validation(self):
         return {"loss": 0.0, "rmse": 0.0, "n": 0}

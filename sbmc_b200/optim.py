@@ -44,6 +44,14 @@ class _CudaBackend(object):
             tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, *scalars,
             th.cuda.current_stream(dev).cuda_stream), "adam")
 
+    def adam_devstep(self, dev, tensors, chunks, nchunks, coef_ptr, lr, beta1, beta2, eps, step):
+        _lib.check(self.lib.sbmc_multi_tensor_adam_devstep_f32(
+            tensors.data_ptr(), chunks.data_ptr(), nchunks, coef_ptr, lr, beta1, beta2, eps,
+            step.data_ptr(), th.cuda.current_stream(dev).cuda_stream), "adam")
+
+    def capturing(self):
+        return th.cuda.is_current_stream_capturing()
+
 
 def _backend():
     return _CudaBackend()
@@ -57,11 +65,68 @@ def _bump_version(p):
 
 
 class FusedAdam(th.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """capturable=True: the step can be captured in a CUDA graph (interfaces.py
+    `cuda_graph`): the step count is ONE device float shared by all parameters
+    (`state[p]["step"]`, like torch.optim.Adam(capturable=True) keeps device steps), the
+    bias corrections are derived from it on the device, and the device tables are built
+    once per set of tensor addresses -- a captured step contains no host-to-device copy,
+    so parameters, gradients and state must keep their addresses (static `.grad`s)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
             raise ValueError("invalid Adam hyper-parameters")
         super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.last_grad_norm = None      # device tensor [2]: norm, clip coefficient
+        self.capturable = bool(capturable)
+        self._dev_step = None
+        self._table_cache = {}          # pointer tuple -> (tensors, chunks, nchunks, partial)
+
+    def _cached_tables(self, rows, dev, backend):
+        key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+                    for p, g, m, v in rows)
+        hit = self._table_cache.get(key)
+        if hit is None:
+            if getattr(backend, "capturing", lambda: False)():
+                raise _lib.SbmcB200Error(
+                    "FusedAdam: tensor addresses changed inside a CUDA-graph capture (run one "
+                    "eager step with the same static gradients first)")
+            tensors, chunks, nchunks = self._tables(rows, dev)
+            partial = th.empty(max(nchunks, 1), dtype=th.float32, device=dev)
+            if len(self._table_cache) > 8:
+                self._table_cache.clear()
+            hit = self._table_cache[key] = (tensors, chunks, nchunks, partial)
+        return hit
+
+    def _step_capturable(self, backend, groups, everything, dev, max_norm):
+        if self._dev_step is None:
+            steps = [self.state[r[0]].get("step") for r in everything]
+            start = max([float(s) for s in steps if s is not None] + [0.0])
+            self._dev_step = th.full((), start, dtype=th.float32, device=dev)
+        for r in everything:
+            self.state[r[0]]["step"] = self._dev_step
+        coef_ptr = None
+        with backend.scope(dev):
+            tensors, chunks, nchunks, partial = self._cached_tables(everything, dev, backend)
+            if max_norm is not None:
+                if self.last_grad_norm is None or self.last_grad_norm.device != dev:
+                    self.last_grad_norm = th.empty(2, dtype=th.float32, device=dev)
+                backend.grad_norm(dev, tensors, chunks, nchunks, partial, float(max_norm),
+                                  self.last_grad_norm)
+                coef_ptr = self.last_grad_norm.data_ptr() + 4
+            if len(groups) == 1:
+                parts = [(groups[0][0], (tensors, chunks, nchunks))]
+            else:
+                parts = [(g, self._cached_tables(rows, dev, backend)[:3]) for g, rows in groups]
+            for i, (group, (tn, ch, nc)) in enumerate(parts):
+                beta1, beta2 = group["betas"]
+                if i + 1 < len(parts):
+                    raise _lib.SbmcB200Error("FusedAdam(capturable=True) supports one "
+                                             "parameter group")
+                backend.adam_devstep(dev, tn, ch, nc, coef_ptr, group["lr"], beta1, beta2,
+                                     group["eps"], self._dev_step)
+            if not getattr(backend, "capturing", lambda: False)():
+                for r in everything:
+                    _bump_version(r[0])
 
     @staticmethod
     def _tables(rows, dev):
@@ -105,7 +170,7 @@ class FusedAdam(th.optim.Optimizer):
                         "FusedAdam wants contiguous float32 CUDA parameters and gradients")
                 state = self.state[p]
                 if not state:
-                    state["step"] = th.zeros((), dtype=th.float32)
+                    state["step"] = th.zeros((), dtype=th.float32) if not self.capturable else None
                     state["exp_avg"] = th.zeros_like(p, memory_format=th.contiguous_format)
                     state["exp_avg_sq"] = th.zeros_like(p, memory_format=th.contiguous_format)
                 rows.append((p, g, state["exp_avg"], state["exp_avg_sq"]))
@@ -117,6 +182,9 @@ class FusedAdam(th.optim.Optimizer):
         dev = everything[0][0].device
         if any(r[0].device != dev for r in everything):
             raise _lib.SbmcB200Error("FusedAdam: all parameters must live on one device")
+        if self.capturable:
+            self._step_capturable(backend, groups, everything, dev, max_norm)
+            return loss
         # tensors that have taken the same number of steps share one launch
         parts = []
         for group, rows in groups:

@@ -90,7 +90,7 @@ def wgrad(dy, x, dw=None, cout_valid=0, cin_valid=0, want_bias=True):
         raise RuntimeError("wgrad: dw must be float32 [cout_valid, cin_valid]")
     db = th.empty(cv, device=dy.device, dtype=th.float32) if want_bias else None
     blocks = (cout // 128) * (cin // 128)
-    nsplit = max(1, min((rows + 127) // 128, (2 * _num_sms(dy.device)) // max(blocks, 1)))
+    nsplit = max(1, min((rows + 127) // 128, _num_sms(dy.device) // max(blocks, 1)))
     ws = th.empty(nsplit * cout * (cin + 1), device=dy.device, dtype=th.float32)
     lib = _lib.load()
     with th.cuda.device(dy.device):
@@ -218,7 +218,7 @@ def colsum(x):
     rows, c = x.shape
     if x.dtype != _BF16 or x.stride(1) != 1:
         raise RuntimeError("colsum: expected bf16 [rows, c] with unit column stride")
-    nblk = max(1, min(2 * _num_sms(x.device), (rows + 63) // 64))
+    nblk = max(1, min(_num_sms(x.device), (rows + 63) // 64))
     ws = th.empty(nblk * c, device=x.device, dtype=th.float32)
     out = th.empty(c, device=x.device, dtype=th.float32)
     lib = _lib.load()

@@ -68,8 +68,13 @@ def main(args):
 
     meta = dict(model_params=model_params, kpcn_mode=args.kpcn_mode, data_params=data_args)
     LOG.info("Model configuration: %s", model_params)
-    interface = interfaces.SampleBasedDenoiserInterface(model, lr=args.lr, cuda=device == "cuda",
-                                                        fused_optimizer=args.fused_optimizer)
+    if args.bf16_train:
+        if not hasattr(model, "bf16_train"):
+            raise SystemExit("--bf16_train serves the sample-based model (not --kpcn_mode)")
+        model.bf16_train = True        # mixed-precision pipeline on the repo's tcgen05 kernels
+    interface = interfaces.SampleBasedDenoiserInterface(
+        model, lr=args.lr, cuda=device == "cuda",
+        fused_optimizer=args.fused_optimizer or args.cuda_graph, cuda_graph=args.cuda_graph)
     checkpointer = _compat.Checkpointer(args.checkpoint_dir, model, meta=meta,
                                         optimizers=interface.optimizer)
     checkpointer.load_latest()
@@ -108,6 +113,12 @@ def parser():
                    help="write a low-spp / output / target / difference gallery every N steps.")
     p.add_argument("--fused_optimizer", action="store_true",
                    help="clip + Adam over all tensors in three launches (extra).")
+    p.add_argument("--bf16_train", action="store_true",
+                   help="mixed-precision training pipeline: bf16 activations, fp32 accumulation "
+                        "and master weights, every GEMM on the tcgen05 kernels (extra).")
+    p.add_argument("--cuda_graph", action="store_true",
+                   help="capture the training step in a CUDA graph per batch shape (extra; "
+                        "implies --fused_optimizer; use with --constant_spp).")
     p.add_argument("--spp", type=int, default=8, help="Max number of samples per pixel.")
     p.add_argument("--kpcn_mode", dest="kpcn_mode", action="store_true", default=False)
     p.add_argument("--gather", dest="gather", action="store_true", default=False)

@@ -45,6 +45,7 @@ int main(void) {
       (entry_fn)sbmc_nchw_to_nhwc_bf16,
       (entry_fn)sbmc_multi_tensor_grad_norm_f32,
       (entry_fn)sbmc_multi_tensor_adam_f32,
+      (entry_fn)sbmc_multi_tensor_adam_devstep_f32,
       (entry_fn)sbmc_lz4_frames_inflate,
       (entry_fn)sbmc_tile_assemble_f32,
       (entry_fn)sbmc_kernel_weighting_fwd_band_f32,

@@ -148,3 +148,40 @@ def test_multisteps_pipeline_is_used_and_close_to_fp32():
     den = sum((want[k] ** 2).sum() for k in want)
     assert (num / den).sqrt().item() < 0.2
     assert all(p.grad is not None and th.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("bf16", [True, False])
+def test_cuda_graph_step_follows_the_eager_step(bf16):
+    """interfaces.SampleBasedDenoiserInterface(cuda_graph=True): three replayed steps on
+    three different batches against the same three steps run eagerly."""
+    from sbmc_b200 import interfaces
+
+    def make():
+        th.manual_seed(1)
+        net = models.Multisteps(12, 3, ksize=5, nsteps=2).cuda().train()
+        net.bf16_train = bf16
+        return net
+    bs, spp, h, w = 2, 2, 32, 48
+    g = th.Generator(device="cuda").manual_seed(5)
+    batches = [{"radiance": th.rand(bs, spp, 3, h, w, device="cuda", generator=g),
+                "features": th.randn(bs, spp, 12, h, w, device="cuda", generator=g),
+                "global_features": th.randn(bs, 3, 1, 1, device="cuda", generator=g),
+                "target_image": th.rand(bs, 3, h, w, device="cuda", generator=g)}
+               for _ in range(3)]
+    eager = interfaces.SampleBasedDenoiserInterface(make(), lr=1e-3, cuda=True, fused_optimizer=True)
+    graph = interfaces.SampleBasedDenoiserInterface(make(), lr=1e-3, cuda=True, fused_optimizer=True,
+                                                    cuda_graph=True)
+    for b in batches:
+        fe, be = eager.train_step(dict(b))
+        fg, bg = graph.train_step(dict(b))
+        assert abs(be["loss"] - bg["loss"]) <= 1e-4 * abs(be["loss"]) + 1e-7
+        assert rel(fg["radiance"], fe["radiance"]) < 1e-4
+    # same arithmetic in both; cuDNN may pick other algorithms under capture, and Adam's
+    # normalised update amplifies last-bit gradient differences on near-zero biases
+    for (k, p), q in zip(eager.model.named_parameters(), graph.model.parameters()):
+        assert rel(q, p) < 5e-3, k
+    num = sum(((q - p) ** 2).sum() for p, q in zip(eager.model.parameters(), graph.model.parameters()))
+    den = sum((p ** 2).sum() for p in eager.model.parameters())
+    assert (num / den).sqrt().item() < 1e-5
+    assert float(graph.optimizer.state[next(graph.model.parameters())]["step"]) == 3.0
+    assert len(graph._graphs) == 1

@@ -271,6 +271,15 @@ SBMC_API int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row_p
                                   float *workspace, float *dw, int64_t ldw, int cout_valid,
                                   int cin_valid, float *db, void *stream);
 
+/* Weight gradient of the 3x3 convolutions (csrc/wgrad.cu): dw9[3 dy + dx][co][ci] (fp32) =
+ * sum_{n,y,x} dp[n][y][x][co] x[n][y + dy - 1][x + dx - 1][ci] (zero outside the image);
+ * dp bf16 [n][h][w][cout], x bf16 [n][h][w][cin]; cout, cin multiples of 128; workspace:
+ * nsplit * 9 * cout * cin floats.  Deterministic split-K tcgen05 GEMM; the reference gets
+ * this gradient from cuDNN through autograd (sbmc/modules.py:248-320). */
+SBMC_API int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n, int h, int w,
+                                     int cout, int cin, int nsplit, float *workspace,
+                                     float *dw9, void *stream);
+
 /* conv3x3 with the activation-derivative mask of sbmc_linear2_nhwc_bf16 in its epilogue
  * (mask bf16 [n][h][w][cout] or NULL): the data-gradient convolutions of the U-net. */
 SBMC_API int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, const float *bias,

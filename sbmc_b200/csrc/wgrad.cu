@@ -214,6 +214,136 @@ wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// 3x3 convolutions (the U-net, sbmc/modules.py:248-320):
+//   dW[3 dy + dx][co][ci] = sum_{n,y,x} dP[n][y][x][co] * X[n][y + dy - 1][x + dx - 1][ci]
+// Same MN-major split-K GEMM; a K chunk is 2 image rows x 64 pixels.  A CTA owns one
+// (co block, ci block, dy): per chunk ONE halo box of X ({64 ch, 66 px, 2 rows}, zero fill
+// = the convolution's padding) serves the three dx taps as three descriptors whose start
+// address is moved by dx rows of 128 bytes (the swizzle is a function of the address), and
+// the three taps accumulate side by side in tensor memory (3 x 128 columns).
+// ---------------------------------------------------------------------------------------
+constexpr int k3Rows = 2, k3Px = 64;
+constexpr int k3ABox = k3Rows * k3Px * 128;                 // 16 KB per 64-channel half
+constexpr int k3BRows = k3Rows * (k3Px + 2);                // 132 box rows
+constexpr int k3BBox = ((k3BRows * 128 + 1023) / 1024) * 1024;   // padded to a swizzle atom: 17 KB
+constexpr int k3Stage = 2 * k3ABox + 2 * k3BBox;
+constexpr int k3Tx = 2 * k3ABox + 2 * k3BRows * 128;
+
+struct Args3 {
+  float *partial;          // [nsplit][9][Cout][Cin]
+  int Cout, Cin, H, W;
+  int tiles_x, tiles_y;
+  long long nchunks;       // n * tiles_y * tiles_x
+  long long chunks_per_split;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H, n}
+                const __grid_constant__ CUtensorMap xmap,      // X  {Cin, W, H, n}
+                const Args3 P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stages = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * k3Stage);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int split = blockIdx.x, dy = blockIdx.z;
+  const int ci_blocks = P.Cin / 128;
+  const int cob = blockIdx.y / ci_blocks, cib = blockIdx.y % ci_blocks;
+  const long long c_lo = (long long)split * P.chunks_per_split;
+  long long c_hi = c_lo + P.chunks_per_split;
+  if (c_hi > P.nchunks) c_hi = P.nchunks;
+  const int nchunks = (c_hi > c_lo) ? (int)(c_hi - c_lo) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ph = 0;
+      int st = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const long long ch = c_lo + c;
+        const int tx = (int)(ch % P.tiles_x);
+        const int ty = (int)((ch / P.tiles_x) % P.tiles_y);
+        const int n = (int)(ch / ((long long)P.tiles_x * P.tiles_y));
+        const int x0 = tx * k3Px, y0 = ty * k3Rows;
+        unsigned char *s = stages + st * k3Stage;
+        mbar_wait(bars + B_EMPTY + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
+        mbar_expect_tx(bars + B_FULL + st, (uint32_t)k3Tx);
+        tma_load_4d(s, &ymap, bars + B_FULL + st, cob * 128, x0, y0, n);
+        tma_load_4d(s + k3ABox, &ymap, bars + B_FULL + st, cob * 128 + 64, x0, y0, n);
+        tma_load_4d(s + 2 * k3ABox, &xmap, bars + B_FULL + st, cib * 128, x0 - 1, y0 + dy - 1, n);
+        tma_load_4d(s + 2 * k3ABox + k3BBox, &xmap, bars + B_FULL + st, cib * 128 + 64, x0 - 1,
+                    y0 + dy - 1, n);
+        st = (st + 1 == kStages) ? 0 : st + 1;
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_bf16_mn(128, 128);
+    const uint64_t dA = desc_mn_sw128(stages, k3ABox);
+    const uint64_t dB = desc_mn_sw128(stages + 2 * k3ABox, k3BBox);
+    uint32_t ph = 0;
+    int st = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(bars + B_FULL + st, (ph >> st) & 1); ph ^= 1u << st;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t a0 = dA + (uint64_t)st * (k3Stage >> 4);
+        const uint64_t b0 = dB + (uint64_t)st * (k3Stage >> 4);
+#pragma unroll
+        for (int r = 0; r < k3Rows; ++r)
+#pragma unroll
+          for (int j = 0; j < k3Px / 16; ++j)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              umma_bf16(tmem + dx * 128, a0 + (uint64_t)((r * k3Px + 16 * j) * 8),
+                        b0 + (uint64_t)((r * (k3Px + 2) + 16 * j + dx) * 8), idesc, (c | r | j) > 0);
+        umma_commit(bars + B_EMPTY + st);
+        if (c == nchunks - 1) umma_commit(bars + B_ACC);
+      }
+      __syncwarp();
+      st = (st + 1 == kStages) ? 0 : st + 1;
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int co = cob * 128 + quad * 32 + lane;
+    if (nchunks > 0) {
+      mbar_wait(bars + B_ACC, 0);
+      tcgen05_fence_after();
+    }
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int dx = 0; dx < 3; ++dx) {
+      float *dst = P.partial + (((long long)split * 9 + 3 * dy + dx) * P.Cout + co) * P.Cin + cib * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        if (nchunks > 0) {
+          tmem_ld_32x32b_x32(lane_base + dx * 128 + c0, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stg256(dst + c0 + 8 * k, reinterpret_cast<const uint32_t *>(v) + 8 * k);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace wg
 }  // namespace sbmc
 
@@ -274,6 +404,74 @@ extern "C" int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row
   const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
   wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a.partial, a.partial_b, nsplit, cout, cin, dw, ldw,
                                                   cout_valid, cin_valid, db);
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  note_path(1);
+  return SBMC_OK;
+}
+
+extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n, int h, int w,
+                                       int cout, int cin, int nsplit, float *workspace,
+                                       float *dw9, void *stream) {
+  using namespace sbmc;
+  if (n < 1 || h < 1 || w < 1 || cout < 1 || cin < 1 || nsplit < 1 || nsplit > 65535) {
+    set_error("wgrad3x3: invalid shape");
+    return SBMC_EINVAL;
+  }
+  if (!dp || !x || !workspace || !dw9) {
+    set_error("wgrad3x3: null pointer argument");
+    return SBMC_EINVAL;
+  }
+  if (cout % 128 != 0 || cin % 128 != 0 || n >= (1ll << 31)) {
+    set_error("wgrad3x3: needs cout %% 128 == 0 and cin %% 128 == 0 (got %d, %d)", cout, cin);
+    return SBMC_EUNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(dp) | reinterpret_cast<uintptr_t>(x) |
+       reinterpret_cast<uintptr_t>(workspace)) & 31) {
+    set_error("wgrad3x3: pointers must be 32-byte aligned");
+    return SBMC_EALIGN;
+  }
+  wg::Args3 a;
+  a.partial = workspace;
+  a.Cout = cout; a.Cin = cin; a.H = h; a.W = w;
+  a.tiles_x = (w + wg::k3Px - 1) / wg::k3Px;
+  a.tiles_y = (h + wg::k3Rows - 1) / wg::k3Rows;
+  a.nchunks = (long long)n * a.tiles_x * a.tiles_y;
+  a.chunks_per_split = ceil_div(a.nchunks, nsplit);
+  CUtensorMap ym, xm;
+  {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)cout * 2 * w, (uint64_t)cout * 2 * w * h};
+    const uint32_t box[4] = {64, (uint32_t)wg::k3Px, (uint32_t)wg::k3Rows, 1};
+    if (!encode_tensor_map_bf16_sw128(&ym, dp, 4, dims, str, box)) return SBMC_ECUDA;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * w, (uint64_t)cin * 2 * w * h};
+    const uint32_t box[4] = {64, (uint32_t)wg::k3Px + 2, (uint32_t)wg::k3Rows, 1};
+    if (!encode_tensor_map_bf16_sw128(&xm, x, 4, dims, str, box)) return SBMC_ECUDA;
+  }
+  const size_t smem = (size_t)wg::kStages * wg::k3Stage + wg::B_COUNT * sizeof(uint64_t) + 16;
+  static bool configured = false;
+  if (!configured) {
+    SBMC_CUDA_OK(cudaFuncSetAttribute(wg::wgrad3x3_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    KernelTimer timer(SBMC_KERNEL_CONV3X3, st);
+    wg::wgrad3x3_kernel<<<dim3((unsigned)nsplit, (cout / 128) * (cin / 128), 3), wg::kThreads, smem,
+                          st>>>(ym, xm, a);
+  }
+  count_launch();
+  SBMC_CUDA_OK(cudaGetLastError());
+  // partial is [nsplit][9 * cout][cin]: the 1x1 reduction with 9 * cout rows
+  const long long total = 9ll * cout * cin;
+  const long long rblocks = (total + 31) / 32;
+  const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
+  wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nullptr, nsplit, 9 * cout, cin, dw9, cin,
+                                                  9 * cout, cin, nullptr);
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
   note_path(1);

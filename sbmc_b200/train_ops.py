@@ -7,7 +7,7 @@ import torch as th
 
 from . import _lib
 
-__all__ = ["linear", "wgrad", "conv3x3", "spp_reduce", "bcast_add", "maxpool2x2_bwd",
+__all__ = ["linear", "wgrad", "wgrad3x3", "conv3x3", "spp_reduce", "bcast_add", "maxpool2x2_bwd",
            "upsample_bwd", "dact", "colsum", "planes_to_rows"]
 
 _BF16 = th.bfloat16
@@ -99,6 +99,27 @@ def wgrad(dy, x, dw=None, cout_valid=0, cin_valid=0, want_bias=True):
                                       _ptr(db), _stream(dy))
     _lib.check(rc, "wgrad")
     return dw, db
+
+
+def wgrad3x3(dp, x):
+    """fp32 [9, cout, cin] weight gradient of a 3x3 / pad 1 convolution, tap = 3 dy + dx:
+    sum over pixels of dp[n, y, x, co] * x[n, y + dy - 1, x + dx - 1, ci] (csrc/wgrad.cu)."""
+    n, h, w, cout = dp.shape
+    cin = x.shape[3]
+    if dp.dtype != _BF16 or x.dtype != _BF16 or not dp.is_contiguous() or not x.is_contiguous() \
+            or tuple(x.shape[:3]) != (n, h, w):
+        raise RuntimeError("wgrad3x3: expected contiguous bf16 [n,h,w,cout] and [n,h,w,cin]")
+    blocks = (cout // 128) * (cin // 128) * 3
+    chunks = n * ((h + 1) // 2) * ((w + 63) // 64)
+    nsplit = max(1, min(chunks, _num_sms(dp.device) // max(blocks, 1)))
+    ws = th.empty(nsplit * 9 * cout * cin, device=dp.device, dtype=th.float32)
+    dw9 = th.empty(9, cout, cin, device=dp.device, dtype=th.float32)
+    lib = _lib.load()
+    with th.cuda.device(dp.device):
+        rc = lib.sbmc_wgrad3x3_nhwc_bf16(dp.data_ptr(), x.data_ptr(), n, h, w, cout, cin, nsplit,
+                                         ws.data_ptr(), dw9.data_ptr(), _stream(dp))
+    _lib.check(rc, "wgrad3x3")
+    return dw9
 
 
 def conv3x3(x, w9, bias, act=0, mask=None, mask_act=0):

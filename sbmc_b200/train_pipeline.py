@@ -19,7 +19,8 @@ repo's kernels:
                 backward  data gradients = the same conv kernel on flipped / transposed
                           weights with the previous layer's activation derivative in the
                           epilogue; max-pool / skip / upsample gradients one kernel each;
-                          weight gradients: cuDNN bf16 (library) for the 3x3 taps
+                          weight gradients on the split-K tcgen05 kernel (csrc/wgrad.cu:
+                          the three dx taps of a kernel row share one halo box)
   RegressStage  kernel_regressor                             (models.py:195-199)
                 the last layer writes fp32 logits as channel planes per sample -- the
                 layout the fused splat reads -- and the backward converts the splat's
@@ -223,9 +224,14 @@ def _upsample_concat(coarse, skip):
     return out
 
 
+OWN_WGRAD3X3 = True      # False: cuDNN's bf16 weight-gradient kernel (A/B comparisons)
+
+
 def _conv_wgrad(dpre, x, cout, cin):
-    """fp32 [cout, cin, 3, 3] weight gradient of a 3x3 convolution from bf16 rows
-    (library call: cuDNN's bf16 weight-gradient kernel)."""
+    """fp32 [cout, cin, 3, 3] weight gradient of a 3x3 convolution from bf16 rows: the
+    split-K tcgen05 kernel of csrc/wgrad.cu (fp32 output)."""
+    if OWN_WGRAD3X3 and cout % 128 == 0 and cin % 128 == 0:
+        return T.wgrad3x3(dpre, x).view(3, 3, cout, cin).permute(2, 3, 0, 1)
     dw = th.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (cout, cin, 3, 3),
                                   dpre.permute(0, 3, 1, 2), padding=1)
     return dw.float()

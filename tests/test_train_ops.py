@@ -193,3 +193,19 @@ def test_planes_to_rows_into_a_row_buffer():
     T.planes_to_rows(g, cpad, out=rows[:, 1], out_img_stride=spp * hw * cpad)
     assert rel(rows[:, 1, :, :c], g.permute(0, 2, 1)) < 3e-3
     assert (rows[:, 1, :, c:] == 0).all() and (rows[:, 0] == 0).all() and (rows[:, 2] == 0).all()
+
+
+@pytest.mark.parametrize("n,h,w,cout,cin", [(2, 16, 64, 128, 128), (1, 17, 70, 128, 256), (3, 8, 32, 256, 128),
+                                            (8, 128, 128, 128, 128), (2, 5, 130, 128, 384)])
+def test_wgrad3x3_matches_conv2d_weight(n, h, w, cout, cin):
+    th.manual_seed(n * h + w)
+    dp = th.randn(n, h, w, cout, device="cuda").to(BF)
+    x = th.randn(n, h, w, cin, device="cuda").to(BF)
+    got = T.wgrad3x3(dp, x)
+    ref = th.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (cout, cin, 3, 3),
+                                   dp.double().permute(0, 3, 1, 2), padding=1)
+    ref9 = ref.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    assert rel(got, ref9) < 1e-5
+    for t in range(9):
+        assert rel(got[t], ref9[t]) < 1e-5, t
+    assert th.equal(got, T.wgrad3x3(dp, x))

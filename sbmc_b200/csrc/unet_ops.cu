@@ -236,7 +236,9 @@ namespace sbmc {
 // reads 2 x 32 consecutive floats of two planes (coalesced) and writes one packed
 // bf16x2 word per pixel into a padded [64][cpad / 2 + 1] tile (conflict-free); the
 // tile is then stored as 64 x cpad x 2 contiguous bytes, 16 bytes per lane.
-constexpr int kT2Px = 128;
+// PX pixels per tile: 128, or 64 for wide outputs (cpad > 256: a 128-pixel tile of 512
+// channels is 132 KB of shared memory, one CTA per SM; 64 pixels keep three resident).
+template <int kT2Px>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64 n, int c,
                          i64 hw, i64 x_img, i64 y_img8, int cpad8) {
@@ -253,12 +255,12 @@ nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64
     const bool full = p0 + kT2Px <= hw;
     // two channel pairs per iteration: 16 independent 128-byte row reads in flight per warp
     for (int cp = 2 * warp; cp < cw; cp += 16) {
-      float a[2][4], b[2][4];
+      float a[2][kT2Px / 32], b[2][kT2Px / 32];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int c0 = 2 * (cp + u);
 #pragma unroll
-        for (int h4 = 0; h4 < 4; ++h4) {
+        for (int h4 = 0; h4 < kT2Px / 32; ++h4) {
           const int px = h4 * 32 + lane;
           const bool ok = (cp + u) < cw_real && (full || p0 + px < hw);
           a[u][h4] = (ok && c0 < c) ? __ldg(src + (i64)c0 * hw + px) : 0.f;
@@ -268,7 +270,7 @@ nchw_to_nhwc_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ y, i64
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int h4 = 0; h4 < 4; ++h4) {
+        for (int h4 = 0; h4 < kT2Px / 32; ++h4) {
           if (cp + u < cw) {
             const __nv_bfloat162 v = __floats2bfloat162_rn(a[u][h4], b[u][h4]);
             tile[(h4 * 32 + lane) * pitch + cp + u] = *reinterpret_cast<const uint32_t *>(&v);
@@ -304,20 +306,27 @@ extern "C" int sbmc_nchw_to_nhwc_bf16(const float *x, int64_t x_img_stride, void
     set_error("nchw_to_nhwc: null or misaligned pointer");
     return SBMC_EINVAL;
   }
-  const i64 tiles = n * ((hw + kT2Px - 1) / kT2Px);
+  const int tpx = cpad > 256 ? 64 : 128;
+  const i64 tiles = n * ((hw + tpx - 1) / tpx);
   i64 blocks = tiles < (i64)num_sms() * 8 ? tiles : (i64)num_sms() * 8;
-  const size_t smem = (size_t)kT2Px * (cpad / 2 + 1) * sizeof(uint32_t);
-  if (smem > 200 * 1024) {
+  const size_t smem = (size_t)tpx * (cpad / 2 + 1) * sizeof(uint32_t);
+  if (smem > 96 * 1024) {
     set_error("nchw_to_nhwc: cpad %d too large", cpad);
     return SBMC_EUNSUPPORTED;
   }
-  SBMC_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_bf16_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBMC_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_bf16_kernel<128>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  SBMC_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_bf16_kernel<64>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_OTHER, st);
-    nchw_to_nhwc_bf16_kernel<<<(unsigned)blocks, 256, smem, st>>>(
-        x, static_cast<uint4 *>(y), n, c, hw, x_img_stride, y_img_stride / 8, cpad / 8);
+    if (tpx == 64)
+      nchw_to_nhwc_bf16_kernel<64><<<(unsigned)blocks, 256, smem, st>>>(
+          x, static_cast<uint4 *>(y), n, c, hw, x_img_stride, y_img_stride / 8, cpad / 8);
+    else
+      nchw_to_nhwc_bf16_kernel<128><<<(unsigned)blocks, 256, smem, st>>>(
+          x, static_cast<uint4 *>(y), n, c, hw, x_img_stride, y_img_stride / 8, cpad / 8);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());

@@ -167,6 +167,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap ymap,      // dY {Cout, rows}
   if (warp == 2) tmem_dealloc(tmem, 256);
 }
 
+// Few splits, many outputs (the 3x3 layers): one thread per 4 consecutive outputs, the
+// splits added in order.  Needs Cin % 4 == 0, contiguous output (ldw == Cin, no trimming).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_vec_kernel(const float4 *__restrict__ partial, int nsplit, long long total4,
+                        float4 *__restrict__ dw) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += 256ll * gridDim.x) {
+    float4 acc = __ldg(partial + i);
+    for (int s = 1; s < nsplit; ++s) {
+      const float4 v = __ldg(partial + s * total4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dw[i] = acc;
+  }
+}
+
 // dw[co][ci] (leading dimension ldw) = sum over the splits, co < cout_valid, ci < cin_valid.
 // Block = 32 consecutive outputs x 8 warps; warp w adds splits w, w + 8, ... (independent
 // coalesced 128-byte loads), the eight partial sums are added in a fixed order.
@@ -223,12 +238,11 @@ wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__
 // address is moved by dx rows of 128 bytes (the swizzle is a function of the address), and
 // the three taps accumulate side by side in tensor memory (3 x 128 columns).
 // ---------------------------------------------------------------------------------------
-constexpr int k3Rows = 2, k3Px = 64;
-constexpr int k3ABox = k3Rows * k3Px * 128;                 // 16 KB per 64-channel half
-constexpr int k3BRows = k3Rows * (k3Px + 2);                // 132 box rows
-constexpr int k3BBox = ((k3BRows * 128 + 1023) / 1024) * 1024;   // padded to a swizzle atom: 17 KB
+// Chunk shapes: 2 rows x 64 pixels, or 4 rows x 32 pixels for images at most 32 wide (the
+// coarsest U-net level of a 128 x 128 crop), so that no half of the box is padding.
+constexpr int k3ABox = 128 * 128;                           // 16 KB per 64-channel half
+constexpr int k3BBox = 17 * 1024;                           // 132 / 136 box rows, padded
 constexpr int k3Stage = 2 * k3ABox + 2 * k3BBox;
-constexpr int k3Tx = 2 * k3ABox + 2 * k3BRows * 128;
 
 struct Args3 {
   float *partial;          // [nsplit][9][Cout][Cin]
@@ -238,6 +252,7 @@ struct Args3 {
   long long chunks_per_split;
 };
 
+template <int k3Px, int k3Rows>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H, n}
                 const __grid_constant__ CUtensorMap xmap,      // X  {Cin, W, H, n}
@@ -279,7 +294,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
         const int x0 = tx * k3Px, y0 = ty * k3Rows;
         unsigned char *s = stages + st * k3Stage;
         mbar_wait(bars + B_EMPTY + st, ((ph >> st) & 1) ^ 1); ph ^= 1u << st;
-        mbar_expect_tx(bars + B_FULL + st, (uint32_t)k3Tx);
+        mbar_expect_tx(bars + B_FULL + st, (uint32_t)(2 * k3ABox + 2 * k3Rows * (k3Px + 2) * 128));
         tma_load_4d(s, &ymap, bars + B_FULL + st, cob * 128, x0, y0, n);
         tma_load_4d(s + k3ABox, &ymap, bars + B_FULL + st, cob * 128 + 64, x0, y0, n);
         tma_load_4d(s + 2 * k3ABox, &xmap, bars + B_FULL + st, cib * 128, x0 - 1, y0 + dy - 1, n);
@@ -427,51 +442,64 @@ extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n,
     return SBMC_EUNSUPPORTED;
   }
   if ((reinterpret_cast<uintptr_t>(dp) | reinterpret_cast<uintptr_t>(x) |
-       reinterpret_cast<uintptr_t>(workspace)) & 31) {
+       reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(dw9)) & 31) {
     set_error("wgrad3x3: pointers must be 32-byte aligned");
     return SBMC_EALIGN;
   }
   wg::Args3 a;
   a.partial = workspace;
   a.Cout = cout; a.Cin = cin; a.H = h; a.W = w;
-  a.tiles_x = (w + wg::k3Px - 1) / wg::k3Px;
-  a.tiles_y = (h + wg::k3Rows - 1) / wg::k3Rows;
+  const int px = (w <= 32) ? 32 : 64, rows = 128 / px;
+  a.tiles_x = (w + px - 1) / px;
+  a.tiles_y = (h + rows - 1) / rows;
   a.nchunks = (long long)n * a.tiles_x * a.tiles_y;
   a.chunks_per_split = ceil_div(a.nchunks, nsplit);
   CUtensorMap ym, xm;
   {
     const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)cout * 2 * w, (uint64_t)cout * 2 * w * h};
-    const uint32_t box[4] = {64, (uint32_t)wg::k3Px, (uint32_t)wg::k3Rows, 1};
+    const uint32_t box[4] = {64, (uint32_t)px, (uint32_t)rows, 1};
     if (!encode_tensor_map_bf16_sw128(&ym, dp, 4, dims, str, box)) return SBMC_ECUDA;
   }
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * w, (uint64_t)cin * 2 * w * h};
-    const uint32_t box[4] = {64, (uint32_t)wg::k3Px + 2, (uint32_t)wg::k3Rows, 1};
+    const uint32_t box[4] = {64, (uint32_t)px + 2, (uint32_t)rows, 1};
     if (!encode_tensor_map_bf16_sw128(&xm, x, 4, dims, str, box)) return SBMC_ECUDA;
   }
   const size_t smem = (size_t)wg::kStages * wg::k3Stage + wg::B_COUNT * sizeof(uint64_t) + 16;
   static bool configured = false;
   if (!configured) {
-    SBMC_CUDA_OK(cudaFuncSetAttribute(wg::wgrad3x3_kernel,
+    SBMC_CUDA_OK(cudaFuncSetAttribute(wg::wgrad3x3_kernel<64, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SBMC_CUDA_OK(cudaFuncSetAttribute(wg::wgrad3x3_kernel<32, 4>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     KernelTimer timer(SBMC_KERNEL_CONV3X3, st);
-    wg::wgrad3x3_kernel<<<dim3((unsigned)nsplit, (cout / 128) * (cin / 128), 3), wg::kThreads, smem,
-                          st>>>(ym, xm, a);
+    const dim3 grid((unsigned)nsplit, (cout / 128) * (cin / 128), 3);
+    if (px == 32)
+      wg::wgrad3x3_kernel<32, 4><<<grid, wg::kThreads, smem, st>>>(ym, xm, a);
+    else
+      wg::wgrad3x3_kernel<64, 2><<<grid, wg::kThreads, smem, st>>>(ym, xm, a);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
-  // partial is [nsplit][9 * cout][cin]: the 1x1 reduction with 9 * cout rows
+  // partial is [nsplit][9 * cout][cin]
   const long long total = 9ll * cout * cin;
-  const long long rblocks = (total + 31) / 32;
-  const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
-  wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nullptr, nsplit, 9 * cout, cin, dw9, cin,
-                                                  9 * cout, cin, nullptr);
+  if (nsplit <= 24) {
+    const long long total4 = total / 4;
+    const long long b = (total4 + 255) / 256;
+    wg::wgrad_reduce_vec_kernel<<<(unsigned)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(workspace), nsplit, total4, reinterpret_cast<float4 *>(dw9));
+  } else {
+    const long long rblocks = (total + 31) / 32;
+    const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
+    wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nullptr, nsplit, 9 * cout, cin, dw9,
+                                                    cin, 9 * cout, cin, nullptr);
+  }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());
   note_path(1);

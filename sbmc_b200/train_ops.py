@@ -110,7 +110,8 @@ def wgrad3x3(dp, x):
             or tuple(x.shape[:3]) != (n, h, w):
         raise RuntimeError("wgrad3x3: expected contiguous bf16 [n,h,w,cout] and [n,h,w,cin]")
     blocks = (cout // 128) * (cin // 128) * 3
-    chunks = n * ((h + 1) // 2) * ((w + 63) // 64)
+    px = 32 if w <= 32 else 64
+    chunks = n * ((h + 128 // px - 1) // (128 // px)) * ((w + px - 1) // px)
     nsplit = max(1, min(chunks, _num_sms(dp.device) // max(blocks, 1)))
     ws = th.empty(nsplit * 9 * cout * cin, device=dp.device, dtype=th.float32)
     dw9 = th.empty(9, cout, cin, device=dp.device, dtype=th.float32)

@@ -178,8 +178,9 @@ def test_cuda_graph_step_follows_the_eager_step(bf16):
         assert rel(fg["radiance"], fe["radiance"]) < 1e-4
     # same arithmetic in both; cuDNN may pick other algorithms under capture, and Adam's
     # normalised update amplifies last-bit gradient differences on near-zero biases
+    # (each of the 3 steps moves a parameter by at most lr = 1e-3)
     for (k, p), q in zip(eager.model.named_parameters(), graph.model.parameters()):
-        assert rel(q, p) < 5e-3, k
+        assert (q - p).abs().max().item() < 1e-4, k
     num = sum(((q - p) ** 2).sum() for p, q in zip(eager.model.parameters(), graph.model.parameters()))
     den = sum((p ** 2).sum() for p in eager.model.parameters())
     assert (num / den).sqrt().item() < 1e-5

@@ -219,6 +219,11 @@ SBMC_API int sbmc_conv3x3_nhwc_bf16(const void *x, const void *w9, const float *
  * (tcgen05.mma.cta_group::2, 4-8 % faster); 0 selects the single-CTA kernel.  Returns
  * the previous value. */
 SBMC_API int sbmc_b200_conv3x3_pair(int flag);
+/* flag != 0 (the default): images at most 85 pixels wide run in the kernel's "linear" mode
+ * (tiles of 256 consecutive pixels of the row-major image with one shared zero column per
+ * row instead of 128-pixel row segments -- the coarse U-net levels of a training crop); 0
+ * selects the row-segment tiling for every width.  Same results.  Returns the previous value. */
+SBMC_API int sbmc_b200_conv3x3_linear(int flag);
 
 /* U-net decoder glue (sbmc/modules.py:314-319): out = cat([bilinear_upsample(low,
  * size=(h, w), align_corners=False), skip], channels) in one pass on bf16

@@ -44,6 +44,7 @@ SIGNATURES = {
                 _int, _int, _int, _int, _ptr, _i64, _i64, _ptr, _i64, _int, _i64, _i64, _i64,
                 _i64, _ptr]),
     "sbmc_b200_conv3x3_pair": (_int, [_int]),
+    "sbmc_b200_conv3x3_linear": (_int, [_int]),
     "sbmc_conv3x3_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_upsample_concat_nhwc_bf16":

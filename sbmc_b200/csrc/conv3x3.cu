@@ -34,6 +34,16 @@
 //   * Epilogue (16 warps): tcgen05.ld -> + bias -> ReLU / LeakyReLU -> bf16 -> 64-byte
 //     vector stores, channels innermost.
 //
+//   * Narrow images ("linear" mode, W <= 85; the coarse U-net levels of a 128 x 128
+//     training crop are 64 and 32 pixels wide, so a 128-pixel tile would be 50-75 %
+//     padding).  The halo box is {64 ch, W + 1 px, R rows}: the column past the image edge
+//     is zero-filled by TMA, so in shared memory the image is ONE sequence of pixels with
+//     a single zero between rows -- which serves both as the right padding of row y and
+//     as the left padding of row y + 1.  A tile is then any 256 consecutive elements of
+//     that sequence (two M = 128 blocks), tap (dy, dx) is the same descriptor moved by
+//     (dy - 1) (W + 1) + (dx - 1) rows, and the epilogue drops the one zero-column
+//     element per image row: W / (W + 1) of the MMA rows are useful.
+//
 // Warp roles: 0 = A producer, 1 = MMA issuer, 2 = TMEM allocation, 3 = B producer,
 // 4..19 = epilogue.
 #include <cuda_bf16.h>
@@ -64,6 +74,10 @@ struct Args {
   int H, W, Cin, Cout;
   int tiles_x, tiles_y, n_img, n_tiles_n;
   long long ntiles;
+  // "linear" mode for narrow images (pitch > 0, single-CTA kernel): see conv3x3_kernel
+  int pitch;               // W + 1: image row + one zero column
+  int slab_rows;           // image rows per halo slab
+  int tiles_img;           // 256-element tiles per image
 };
 
 enum { B_AF = 0, B_AE = 2, B_BF = 4, B_BE = 4 + kMaxStages, B_ACCF = 4 + 2 * kMaxStages,
@@ -97,9 +111,33 @@ static bool pair_enabled() {
   return g_pair != 0;
 }
 
+// Widest image served by the linear mode: its slab, ceil((257 + 3 (W + 1)) / (W + 1)) rows
+// of W + 1 pixels, must fit the 520 rows of a halo slab.  SBMC_B200_CONV_LINEAR=0 disables
+// the mode (A/B runs).
+constexpr int kLinearMaxW = 85;
+static int g_linear = -1;
+static bool linear_enabled() {
+  if (g_linear < 0) {
+    const char *e = getenv("SBMC_B200_CONV_LINEAR");
+    g_linear = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_linear != 0;
+}
+
 struct TileCoord { int n, y0, x0, n0; };
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 __device__ __forceinline__ TileCoord tile_coord(long long tile, const Args &P, int nt) {
   TileCoord t;
+  if (P.pitch > 0) {
+    // linear mode: x0 = first element of the tile in the image's [H][W + 1] numbering,
+    // y0 = first image row of its halo slab (may be negative: zero fill)
+    const int tl = (int)(tile % P.tiles_img); tile /= P.tiles_img;
+    t.n = (int)(tile % P.n_img); tile /= P.n_img;
+    t.n0 = (int)tile * nt;
+    t.x0 = tl * 256;
+    t.y0 = floor_div(t.x0 - P.pitch - 1, P.pitch);
+    return t;
+  }
   const int tx = (int)(tile % P.tiles_x); tile /= P.tiles_x;
   const int ty = (int)(tile % P.tiles_y); tile /= P.tiles_y;
   t.n = (int)(tile % P.n_img); tile /= P.n_img;
@@ -153,8 +191,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
         const TileCoord t = tile_coord(tile, P, NT);
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + B_AE + ab, ((ph >> ab) & 1) ^ 1); ph ^= 1u << ab;
-          mbar_expect_tx(bars + B_AF + ab, (uint32_t)kASlab);
-          tma_load_4d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, t.x0 - 1, t.y0 - 1, t.n);
+          if (P.pitch > 0) {
+            mbar_expect_tx(bars + B_AF + ab, (uint32_t)(P.slab_rows * P.pitch * 128));
+            tma_load_4d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, 0, t.y0, t.n);
+          } else {
+            mbar_expect_tx(bars + B_AF + ab, (uint32_t)kASlab);
+            tma_load_4d(sA + ab * kASlab, &amap, bars + B_AF + ab, s * 64, t.x0 - 1, t.y0 - 1, t.n);
+          }
           ab ^= 1;
         }
       }
@@ -186,6 +229,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
       int ab = 0, st = 0, it = 0;
       for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
         const int buf = (NT == 128) ? (it & 1) : 0;
+        // slab row of tap (0, 0) of row block 0, and the row distance between dy taps /
+        // row blocks (linear mode: elements of the [H][W + 1] sequence)
+        int base_row = 0, dy_rows = kHaloW, g_rows = kHaloW;
+        if (P.pitch > 0) {
+          const TileCoord t = tile_coord(tile, P, NT);
+          base_row = t.x0 - t.y0 * P.pitch - P.pitch - 1;
+          dy_rows = P.pitch;
+          g_rows = 128;
+        }
         mbar_wait(bars + B_ACCE + buf, ((ph_acc >> buf) & 1) ^ 1); ph_acc ^= 1u << buf;
         for (int s = 0; s < nslabs; ++s) {
           mbar_wait(bars + B_AF + ab, (ph_a >> ab) & 1); ph_a ^= 1u << ab;
@@ -200,7 +252,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
               const uint64_t bd0 = dB + (uint64_t)st * (kBStage >> 4);
 #pragma unroll
               for (int g = 0; g < kRows; ++g) {
-                const uint64_t ad0 = da + (uint64_t)(((g + dy) * kHaloW + dx) * kRowD);
+                const uint64_t ad0 =
+                    da + (uint64_t)((base_row + g * g_rows + dy * dy_rows + dx) * kRowD);
                 const uint32_t d = tmem + ((NT == 128) ? buf * 256 + g * 128 : g * 256);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -240,14 +293,21 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
       // 64 channels per step: 2 x tcgen05.ld -> bias, activation -> 32 packed words ->
       // transpose inside the lane quad -> 4 x 256-bit stores that each complete 8 lines
       // (umma.cuh::quad_transpose32; one 16-byte store per lane would touch 32 lines)
-      const int y = t.y0 + g;
-      const int xq = t.x0 + px - (lane & 3);            // first pixel of this lane's quad
+      int y = t.y0 + g;
+      int xq = t.x0 + px - (lane & 3);                  // first pixel of this lane's quad
+      int xown = t.x0 + px;
+      if (P.pitch > 0) {
+        const int e = t.x0 + g * 128 + px;              // element of the [H][W + 1] sequence
+        y = e / P.pitch;
+        xown = e - y * P.pitch;                         // == W: the zero column, dropped
+        xq = xown - (lane & 3);
+      }
       __nv_bfloat16 *dst = P.out + (((long long)t.n * P.H + y) * P.W + xq) * P.Cout + t.n0 +
                            (lane & 3) * 16;
       const float *bias = P.bias + t.n0;
       const __nv_bfloat16 *mrow = nullptr;
-      if (P.mask && y < P.H && t.x0 + px < P.W)
-        mrow = P.mask + (((long long)t.n * P.H + y) * P.W + t.x0 + px) * P.Cout + t.n0;
+      if (P.mask && y < P.H && xown < P.W)
+        mrow = P.mask + (((long long)t.n * P.H + y) * P.W + xown) * P.Cout + t.n0;
       const float mslope = (P.mask_act == 2) ? 0.01f : 0.f;
 #pragma unroll 1
       for (int c0 = part * (NT / 2); c0 < (part + 1) * (NT / 2); c0 += 64) {
@@ -273,7 +333,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
             q[16 * hh + 2 * q4 + 1] = pack_bf16(u2, u3);
           }
         }
-        if (NT == 256) {
+        if (NT == 256 && P.pitch == 0) {
           // the epilogue runs after the tile's last MMA: the shuffles have the shared-memory
           // crossbar to themselves
           quad_transpose32(q, lane);
@@ -287,7 +347,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap amap,      // input  {Cin, W,
           // already saturate the shared-memory data path that shuffles share (measured:
           // the transposed variant made the 128 -> 128 layer 30 % slower,
           // profiles/r2f_convs.jsonl): plain 256-bit stores of the thread's own row
-          if (y < P.H && xq + (lane & 3) < P.W) {
+          if (y < P.H && xown < P.W) {
             __nv_bfloat16 *own = dst - (lane & 3) * 16 + (long long)(lane & 3) * P.Cout + c0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) stg256(own + 16 * k, q + 8 * k);
@@ -582,6 +642,12 @@ static int launch(const Args &a, const CUtensorMap &am, const CUtensorMap &wm, c
 }  // namespace c3
 }  // namespace sbmc
 
+extern "C" int sbmc_b200_conv3x3_linear(int flag) {
+  const int prev = sbmc::c3::linear_enabled() ? 1 : 0;
+  sbmc::c3::g_linear = flag ? 1 : 0;
+  return prev;
+}
+
 extern "C" int sbmc_b200_conv3x3_pair(int flag) {
   const int prev = sbmc::c3::pair_enabled() ? 1 : 0;
   sbmc::c3::g_pair = flag ? 1 : 0;
@@ -633,11 +699,20 @@ extern "C" int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, cons
   a.n_img = (int)n;
   a.n_tiles_n = cout / nt;
   a.ntiles = (long long)a.tiles_x * a.tiles_y * n * a.n_tiles_n;
+  a.pitch = 0; a.slab_rows = 0; a.tiles_img = 0;
+  if (w <= c3::kLinearMaxW && c3::linear_enabled()) {
+    // narrow image: tiles of 256 consecutive elements of the [H][W + 1] sequence
+    a.pitch = w + 1;
+    a.slab_rows = (257 + 3 * a.pitch + a.pitch - 1) / a.pitch;
+    a.tiles_img = (h * a.pitch + 255) / 256;
+    a.ntiles = (long long)a.tiles_img * n * a.n_tiles_n;
+  }
   CUtensorMap am, wm;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * w, (uint64_t)cin * 2 * w * h};
-    const uint32_t box[4] = {64, c3::kHaloW, c3::kHaloH, 1};
+    const uint32_t box[4] = {64, a.pitch ? (uint32_t)a.pitch : c3::kHaloW,
+                             a.pitch ? (uint32_t)a.slab_rows : c3::kHaloH, 1};
     if (!encode_tensor_map_bf16_sw128(&am, x, 4, dims, str, box)) return SBMC_ECUDA;
   }
   {
@@ -648,7 +723,7 @@ extern "C" int sbmc_conv3x3_masked_nhwc_bf16(const void *x, const void *w9, cons
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   note_path(1);
-  if (nt == 128 && cout == 128 && c3::pair_enabled()) {
+  if (nt == 128 && cout == 128 && a.pitch == 0 && c3::pair_enabled()) {
     // CTA pairs (cta_group::2): each CTA loads 64 of the 128 output channels per stage
     CUtensorMap wh;
     const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};

@@ -29,6 +29,7 @@ int main(void) {
       (entry_fn)sbmc_chain_samples_nhwc_bf16,
       (entry_fn)sbmc_conv3x3_nhwc_bf16,
       (entry_fn)sbmc_b200_conv3x3_pair,
+      (entry_fn)sbmc_b200_conv3x3_linear,
       (entry_fn)sbmc_maxpool2x2_nhwc_bf16,
       (entry_fn)sbmc_linear_nhwc_bf16,
       (entry_fn)sbmc_linear2_nhwc_bf16,

@@ -21,7 +21,8 @@ def test_prepare_weight_layout():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cin,cout", [(128, 128), (64, 256), (384, 128), (256, 512)])
-@pytest.mark.parametrize("n,h,w", [(1, 8, 128), (2, 7, 45), (1, 33, 300), (3, 2, 129)])
+@pytest.mark.parametrize("n,h,w", [(1, 8, 128), (2, 7, 45), (1, 33, 300), (3, 2, 129),
+                                   (4, 32, 32), (2, 64, 64), (1, 9, 85), (2, 5, 3), (1, 1, 1)])
 @pytest.mark.parametrize("act", [0, 2])
 def test_conv3x3_matches_torch(cin, cout, n, h, w, act):
     th.manual_seed(cin + cout + h + w)
@@ -98,6 +99,28 @@ def test_upsample_concat_and_layout_change_kernels_after_their_rewrite():
         want = th.zeros(shape[:-3] + (h * w, 128), device="cuda", dtype=th.bfloat16)
         want[..., :c] = x.reshape(shape[:-3] + (c, h * w)).transpose(-1, -2)
         assert th.equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", [(128, 128), (128, 256)])
+@pytest.mark.parametrize("n,h,w", [(8, 32, 32), (2, 64, 64), (1, 9, 85), (3, 7, 20)])
+def test_linear_mode_gives_the_same_result(cin, cout, n, h, w):
+    """Narrow images: tiles of 256 consecutive pixels of the [H][W + 1] sequence against
+    the 128-pixel row-segment tiling (same accumulation order: bit-identical)."""
+    from sbmc_b200 import _lib
+    th.manual_seed(6)
+    x = th.randn(n, h, w, cin, device="cuda").to(th.bfloat16)
+    w9 = conv3x3.prepare_weight((th.randn(cout, cin, 3, 3, device="cuda") / 34.0).to(th.bfloat16))
+    bias = th.randn(cout, device="cuda")
+    lib = _lib.load()
+    prev = lib.sbmc_b200_conv3x3_linear(0)
+    try:
+        tiled = conv3x3.conv3x3_nhwc(x, w9, bias, act=1)
+        lib.sbmc_b200_conv3x3_linear(1)
+        linear = conv3x3.conv3x3_nhwc(x, w9, bias, act=1)
+    finally:
+        lib.sbmc_b200_conv3x3_linear(prev)
+    assert th.equal(tiled, linear)
 
 
 @pytest.mark.gpu

@@ -17,7 +17,12 @@ HBM = 6551e9
 TENSOR = 1644e12
 
 
+NCU = "--ncu" in sys.argv          # one launch per kernel, no library references
+
+
 def timed(fn, warm=3, reps=20):
+    if NCU:
+        warm, reps = 0, 1
     for _ in range(warm):
         fn()
     th.cuda.synchronize()
@@ -68,11 +73,11 @@ def main():
         x, w3, b3, 0, hw=h * w, spp=spp, out_mode=2, out=logits, out_img_stride=441 * h * w,
         out_smp_stride=bs * 441 * h * w, cout_valid=441)), bytes_=S * (256 + 441 * 4))
     dy = th.randn(S, 128, device=dev).to(BF)
-    t_ref = timed(lambda: th.matmul(dy.t(), x))
+    t_ref = None if NCU else timed(lambda: th.matmul(dy.t(), x))
     line("wgrad 1x1 128x128 over S rows (+ bias gradient)", timed(lambda: T.wgrad(dy, x)),
          bytes_=S * 512, ref_ms=t_ref, ref="cublas_bf16_matmul_ms")
     dy5 = th.randn(S, 512, device=dev).to(BF)
-    t_ref = timed(lambda: th.matmul(dy5.t(), x))
+    t_ref = None if NCU else timed(lambda: th.matmul(dy5.t(), x))
     line("wgrad 1x1 512x128 over S rows (regressor)", timed(lambda: T.wgrad(dy5, x, cout_valid=441)),
          bytes_=S * (1024 + 256), ref_ms=t_ref, ref="cublas_bf16_matmul_ms")
     del dy5
@@ -90,9 +95,10 @@ def main():
         xx = th.randn(bs, hh, hh, cin, device=dev).to(BF)
         dp = th.randn(bs, hh, hh, cout, device=dev).to(BF)
         flops = 2.0 * 9 * cin * cout * bs * hh * hh
-        t_ref = timed(lambda: th.nn.grad.conv2d_weight(xx.permute(0, 3, 1, 2), (cout, cin, 3, 3),
-                                                       dp.permute(0, 3, 1, 2), padding=1))
-        line("wgrad3x3 %d->%d @ %dx%d x8" % (cin, cout, hh, hh), timed(lambda: T.wgrad3x3(dp, xx)),
+        t_ref = None if NCU else timed(lambda: th.nn.grad.conv2d_weight(
+            xx.permute(0, 3, 1, 2), (cout, cin, 3, 3), dp.permute(0, 3, 1, 2), padding=1))
+        line("wgrad3x3 %d->%d @ %dx%d x8 (+ bias gradient)" % (cin, cout, hh, hh),
+             timed(lambda: T.wgrad3x3(dp, xx, want_bias=True)),
              flops=flops, ref_ms=t_ref, ref="cudnn_bf16_wgrad_ms")
         w9 = th.randn(9, cout, cin, device=dev).to(BF)
         zb = th.zeros(cout, device=dev)

@@ -278,12 +278,22 @@ SBMC_API int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row_p
 
 /* Weight gradient of the 3x3 convolutions (csrc/wgrad.cu): dw9[3 dy + dx][co][ci] (fp32) =
  * sum_{n,y,x} dp[n][y][x][co] x[n][y + dy - 1][x + dx - 1][ci] (zero outside the image);
- * dp bf16 [n][h][w][cout], x bf16 [n][h][w][cin]; cout, cin multiples of 128; workspace:
- * nsplit * 9 * cout * cin floats.  Deterministic split-K tcgen05 GEMM; the reference gets
- * this gradient from cuDNN through autograd (sbmc/modules.py:248-320). */
+ * and db[co] = sum dp[n][y][x][co] (db may be NULL); dp bf16 [n][h][w][cout], x bf16
+ * [n][h][w][cin]; cout, cin multiples of 128; workspace: nsplit * cout * (9 * cin + 1) floats.
+ * Deterministic split-K tcgen05 GEMM; the reference gets these gradients from cuDNN through
+ * autograd (sbmc/modules.py:248-320). */
 SBMC_API int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n, int h, int w,
                                      int cout, int cin, int nsplit, float *workspace,
-                                     float *dw9, void *stream);
+                                     float *dw9, float *db, void *stream);
+
+/* Weight normalization of all convolutions of a model in one launch (csrc/weight_bank.cu;
+ * the reference wraps every convolution in nn.utils.weight_norm, sbmc/modules.py:84-87,
+ * 176-179).  entries int64 [ne][16] = {v, g, F, D, 1/|v|, dW, dv, dg pointers, cout, cin, T,
+ * cout_pad, cin_pad, 0, 0, 0}; blocks int64 [nblocks][2] = {entry, first output channel} (8
+ * channels per block).  backward == 0: v, g -> bf16 operands F [T][cout_pad][cin_pad] and D
+ * (data-gradient layout) + 1/|v|; backward != 0: dW fp32 [T][cout][cin] -> dv, dg. */
+SBMC_API int sbmc_weight_bank_run(const int64_t *entries, const int64_t *blocks, int64_t nblocks,
+                                  int backward, void *stream);
 
 /* conv3x3 with the activation-derivative mask of sbmc_linear2_nhwc_bf16 in its epilogue
  * (mask bf16 [n][h][w][cout] or NULL): the data-gradient convolutions of the U-net. */

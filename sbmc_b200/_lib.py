@@ -58,7 +58,8 @@ SIGNATURES = {
         (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _int, _ptr, _ptr, _i64, _int, _int, _ptr,
                 _ptr]),
     "sbmc_wgrad3x3_nhwc_bf16":
-        (_int, [_ptr, _ptr, _i64, _int, _int, _int, _int, _int, _ptr, _ptr, _ptr]),
+        (_int, [_ptr, _ptr, _i64, _int, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr]),
+    "sbmc_weight_bank_run": (_int, [_ptr, _ptr, _i64, _int, _ptr]),
     "sbmc_conv3x3_masked_nhwc_bf16":
         (_int, [_ptr, _ptr, _ptr, _ptr, _int, _ptr, _i64, _int, _int, _int, _int, _int, _ptr]),
     "sbmc_spp_reduce_nhwc_bf16": (_int, [_ptr, _ptr, _int, _i64, _int, _i64, _int, _f32, _ptr]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libsbmc_b200.so")
 SOURCES = ["runtime.cu", "generic.cu", "kw_launch.cu", "s2g.cu", "capi.cu",
-           "host_stream.cu", "splat.cu", "splat_bwd.cu", "conv1x1.cu", "chain_v3.cu", "conv3x3.cu", "linear.cu", "wgrad.cu", "train_ops.cu", "unet_ops.cu", "tiles.cu", "optim.cu"]
+           "host_stream.cu", "splat.cu", "splat_bwd.cu", "conv1x1.cu", "chain_v3.cu", "conv3x3.cu", "linear.cu", "wgrad.cu", "train_ops.cu", "weight_bank.cu", "unet_ops.cu", "tiles.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
     "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

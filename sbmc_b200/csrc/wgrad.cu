@@ -171,7 +171,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap ymap,      // dY {Cout, rows}
 // splits added in order.  Needs Cin % 4 == 0, contiguous output (ldw == Cin, no trimming).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_vec_kernel(const float4 *__restrict__ partial, int nsplit, long long total4,
-                        float4 *__restrict__ dw) {
+                        float4 *__restrict__ dw, const float *__restrict__ partial_b, int cout,
+                        float *__restrict__ db) {
+  if (db && blockIdx.x == gridDim.x - 1) {
+    for (int co = threadIdx.x; co < cout; co += 256) {
+      float acc = 0.f;
+      for (int s = 0; s < nsplit; ++s) acc += partial_b[(long long)s * cout + co];
+      db[co] = acc;
+    }
+  }
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += 256ll * gridDim.x) {
     float4 acc = __ldg(partial + i);
     for (int s = 1; s < nsplit; ++s) {
@@ -246,6 +254,7 @@ constexpr int k3Stage = 2 * k3ABox + 2 * k3BBox;
 
 struct Args3 {
   float *partial;          // [nsplit][9][Cout][Cin]
+  float *partial_b;        // [nsplit][Cout] or null: bias gradient (sum of dP over the pixels)
   int Cout, Cin, H, W;
   int tiles_x, tiles_y;
   long long nchunks;       // n * tiles_y * tiles_x
@@ -259,7 +268,8 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
                 const Args3 P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *stages = smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * k3Stage);
+  unsigned char *ones = smem + kStages * k3Stage;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ones + kOnes);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -267,6 +277,9 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
   const int split = blockIdx.x, dy = blockIdx.z;
   const int ci_blocks = P.Cin / 128;
   const int cob = blockIdx.y / ci_blocks, cib = blockIdx.y % ci_blocks;
+  // the bias gradient rides on the (ci block 0, dy 0) CTAs: one N = 16 MMA per K step
+  // against a block of ones (columns 384..399 of tensor memory)
+  const bool with_bias = P.partial_b != nullptr && cib == 0 && dy == 0;
   const long long c_lo = (long long)split * P.chunks_per_split;
   long long c_hi = c_lo + P.chunks_per_split;
   if (c_hi > P.nchunks) c_hi = P.nchunks;
@@ -276,6 +289,9 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
     for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < kOnes / 4; i += kThreads)
+    reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;      // bf16 1.0 pairs
+  fence_proxy_async();
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tcgen05_fence_before();
   __syncthreads();
@@ -304,9 +320,10 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_bf16_mn(128, 128);
+    const uint32_t idesc = idesc_bf16_mn(128, 128), idesc1 = idesc_bf16_mn(128, 16);
     const uint64_t dA = desc_mn_sw128(stages, k3ABox);
     const uint64_t dB = desc_mn_sw128(stages + 2 * k3ABox, k3BBox);
+    const uint64_t dOnes = desc_mn_sw128(ones, 0);
     uint32_t ph = 0;
     int st = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -318,11 +335,15 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
 #pragma unroll
         for (int r = 0; r < k3Rows; ++r)
 #pragma unroll
-          for (int j = 0; j < k3Px / 16; ++j)
+          for (int j = 0; j < k3Px / 16; ++j) {
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx)
               umma_bf16(tmem + dx * 128, a0 + (uint64_t)((r * k3Px + 16 * j) * 8),
                         b0 + (uint64_t)((r * (k3Px + 2) + 16 * j + dx) * 8), idesc, (c | r | j) > 0);
+            if (with_bias)
+              umma_bf16(tmem + 384, a0 + (uint64_t)((r * k3Px + 16 * j) * 8), dOnes, idesc1,
+                        (c | r | j) > 0);
+          }
         umma_commit(bars + B_EMPTY + st);
         if (c == nchunks - 1) umma_commit(bars + B_ACC);
       }
@@ -352,6 +373,12 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap ymap,      // dP {Cout, W, H
 #pragma unroll
         for (int k = 0; k < 4; ++k) stg256(dst + c0 + 8 * k, reinterpret_cast<const uint32_t *>(v) + 8 * k);
       }
+    }
+    if (with_bias) {
+      float v[32];
+      v[0] = 0.f;
+      if (nchunks > 0) tmem_ld_32x32b_x32(lane_base + 384, v);
+      P.partial_b[(long long)split * P.Cout + co] = v[0];
     }
   }
   tcgen05_fence_before();
@@ -427,7 +454,7 @@ extern "C" int sbmc_wgrad_nhwc_bf16(const void *dy, const void *x, int64_t x_row
 
 extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n, int h, int w,
                                        int cout, int cin, int nsplit, float *workspace,
-                                       float *dw9, void *stream) {
+                                       float *dw9, float *db, void *stream) {
   using namespace sbmc;
   if (n < 1 || h < 1 || w < 1 || cout < 1 || cin < 1 || nsplit < 1 || nsplit > 65535) {
     set_error("wgrad3x3: invalid shape");
@@ -448,6 +475,7 @@ extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n,
   }
   wg::Args3 a;
   a.partial = workspace;
+  a.partial_b = db ? workspace + (size_t)nsplit * 9 * cout * cin : nullptr;
   a.Cout = cout; a.Cin = cin; a.H = h; a.W = w;
   const int px = (w <= 32) ? 32 : 64, rows = 128 / px;
   a.tiles_x = (w + px - 1) / px;
@@ -467,7 +495,7 @@ extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n,
     const uint32_t box[4] = {64, (uint32_t)px + 2, (uint32_t)rows, 1};
     if (!encode_tensor_map_bf16_sw128(&xm, x, 4, dims, str, box)) return SBMC_ECUDA;
   }
-  const size_t smem = (size_t)wg::kStages * wg::k3Stage + wg::B_COUNT * sizeof(uint64_t) + 16;
+  const size_t smem = (size_t)wg::kStages * wg::k3Stage + wg::kOnes + wg::B_COUNT * sizeof(uint64_t) + 16;
   static bool configured = false;
   if (!configured) {
     SBMC_CUDA_OK(cudaFuncSetAttribute(wg::wgrad3x3_kernel<64, 2>,
@@ -493,12 +521,16 @@ extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n,
     const long long total4 = total / 4;
     const long long b = (total4 + 255) / 256;
     wg::wgrad_reduce_vec_kernel<<<(unsigned)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(workspace), nsplit, total4, reinterpret_cast<float4 *>(dw9));
+        reinterpret_cast<const float4 *>(workspace), nsplit, total4, reinterpret_cast<float4 *>(dw9),
+        a.partial_b, cout, db);
   } else {
     const long long rblocks = (total + 31) / 32;
     const unsigned blocks = (unsigned)(rblocks > 148 * 8 ? 148 * 8 : rblocks);
     wg::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nullptr, nsplit, 9 * cout, cin, dw9,
                                                     cin, 9 * cout, cin, nullptr);
+    if (db)      // bias partials: the generic reduction with zero weight outputs (cin_valid = 0)
+      wg::wgrad_reduce_kernel<<<(cout + 31) / 32, 256, 0, st>>>(workspace, a.partial_b, nsplit, cout,
+                                                               cin, dw9, cin, cout, 0, db);
   }
   count_launch();
   SBMC_CUDA_OK(cudaGetLastError());

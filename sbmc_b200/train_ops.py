@@ -101,9 +101,10 @@ def wgrad(dy, x, dw=None, cout_valid=0, cin_valid=0, want_bias=True):
     return dw, db
 
 
-def wgrad3x3(dp, x):
+def wgrad3x3(dp, x, out=None, want_bias=False):
     """fp32 [9, cout, cin] weight gradient of a 3x3 / pad 1 convolution, tap = 3 dy + dx:
-    sum over pixels of dp[n, y, x, co] * x[n, y + dy - 1, x + dx - 1, ci] (csrc/wgrad.cu)."""
+    sum over pixels of dp[n, y, x, co] * x[n, y + dy - 1, x + dx - 1, ci] (csrc/wgrad.cu);
+    with want_bias: (dw9, db), db[co] = sum over pixels of dp (from the same kernel)."""
     n, h, w, cout = dp.shape
     cin = x.shape[3]
     if dp.dtype != _BF16 or x.dtype != _BF16 or not dp.is_contiguous() or not x.is_contiguous() \
@@ -113,14 +114,17 @@ def wgrad3x3(dp, x):
     px = 32 if w <= 32 else 64
     chunks = n * ((h + 128 // px - 1) // (128 // px)) * ((w + px - 1) // px)
     nsplit = max(1, min(chunks, _num_sms(dp.device) // max(blocks, 1)))
-    ws = th.empty(nsplit * 9 * cout * cin, device=dp.device, dtype=th.float32)
-    dw9 = th.empty(9, cout, cin, device=dp.device, dtype=th.float32)
+    ws = th.empty(nsplit * cout * (9 * cin + 1), device=dp.device, dtype=th.float32)
+    db = th.empty(cout, device=dp.device, dtype=th.float32) if want_bias else None
+    dw9 = out if out is not None else th.empty(9, cout, cin, device=dp.device, dtype=th.float32)
+    if dw9.dtype != th.float32 or tuple(dw9.shape) != (9, cout, cin) or not dw9.is_contiguous():
+        raise RuntimeError("wgrad3x3: out must be contiguous float32 [9, cout, cin]")
     lib = _lib.load()
     with th.cuda.device(dp.device):
         rc = lib.sbmc_wgrad3x3_nhwc_bf16(dp.data_ptr(), x.data_ptr(), n, h, w, cout, cin, nsplit,
-                                         ws.data_ptr(), dw9.data_ptr(), _stream(dp))
+                                         ws.data_ptr(), dw9.data_ptr(), _ptr(db), _stream(dp))
     _lib.check(rc, "wgrad3x3")
-    return dw9
+    return (dw9, db) if want_bias else dw9
 
 
 def conv3x3(x, w9, bias, act=0, mask=None, mask_act=0):

@@ -27,7 +27,10 @@ repo's kernels:
                 plane gradients back to bf16 rows in one pass per sample
   splat         modules.ProgressiveKernelApply (fused fp32 forward / backward kernels)
 
-Weight normalization, the loss and the optimizer stay ordinary PyTorch / FusedAdam.
+Weight normalization of all 57 convolutions is ONE node (`weight_bank.WeightBank`: one
+launch prepares every bf16 operand in both layouts, one launch turns all weight gradients
+into the gradients of weight_v / weight_g).  The loss stays ordinary PyTorch, the optimizer
+is FusedAdam.
 Gradients carry bf16 rounding of the activations (a few percent in norm against the
 fp32 module after ~40 layers; tests/test_train_pipeline.py states the bars), so this
 is not the default training path.
@@ -37,96 +40,106 @@ import torch as th
 from . import _lib
 from . import train_ops as T
 from ._compat import crop_like
+from .weight_bank import WeightBank
 
-__all__ = ["supported", "forward_train", "EmbedStage", "RegressStage", "UNetStage"]
+__all__ = ["supported", "forward_train", "EmbedStage", "RegressStage", "UNetStage", "WeightBank",
+           "chain_specs", "unet_specs", "embed_stage", "regress_stage", "unet_stage"]
 
 BF = th.bfloat16
 _ACT = {th.nn.ReLU: 1, th.nn.LeakyReLU: 2}
 
 
-# -- parameter plumbing (differentiable torch ops on tiny tensors) ------------------------
-def _eff_weight(conv):
-    if hasattr(conv, "weight_g") and hasattr(conv, "weight_v"):
-        return th._weight_norm(conv.weight_v, conv.weight_g, 0)
-    return conv.weight
-
-
+# -- the weight bank of a model ---------------------------------------------------------------
 def _chain_convs(chain):
     from .conv1x1 import _convs
     return _convs(chain)
 
 
-def _chain_params(chain, cin_pad):
-    """fp32 (w1 [128, cin_pad], b1, w2, b2, w3 [cout, 128], b3, act) of a depth-3 1x1 chain as
-    differentiable functions of its parameters; w1's input channels zero-padded."""
+def _chain_act(chain):
+    return 2 if isinstance(chain.layer_0.layer[1], th.nn.LeakyReLU) else 1
+
+
+def chain_specs(chain, cin_pad, cout_pad=0):
+    """Bank specs of a depth-3 1x1 chain: layer 1's input channels padded to cin_pad, the
+    prediction's output channels to cout_pad."""
     c1, c2, c3 = _chain_convs(chain)
-    w = [_eff_weight(c).reshape(c.out_channels, c.in_channels) for c in (c1, c2, c3)]
-    if w[0].shape[1] < cin_pad:
-        w[0] = th.nn.functional.pad(w[0], (0, cin_pad - w[0].shape[1]))
-    act = 2 if isinstance(chain.layer_0.layer[1], th.nn.LeakyReLU) else 1
-    return w[0], c1.bias, w[1], c2.bias, w[2], c3.bias, act
+    return [(c1, cin_pad, 0), (c2, 0, 0), (c3, 0, cout_pad)]
 
 
-def _bf(t):
-    return t.detach().to(BF).contiguous()
+def unet_specs(autoencoder):
+    plan = _unet_plan(autoencoder)
+    return plan, [(conv, 0, 0) for left, right in plan for conv, _ in left + (right or [])]
 
 
-def _t(w):
-    """bf16 [cin, cout] transpose of an fp32 / bf16 [cout, cin] weight (data-gradient GEMM)."""
-    return w.detach().t().to(BF).contiguous()
+def _model_bank(model, nf, ngf):
+    """(bank, index) of a Multisteps model; cached on the model, rebuilt when a parameter
+    moved.  index: {"embed": [(k1, k2, k3)], "unet": [(plan, [k...])], "reg": (k1, k2, k3)}."""
+    specs, index = [], {"embed": [], "unet": []}
+    for step in range(model.nsteps):
+        k = len(specs)
+        specs += chain_specs(getattr(model, "embedding_{:02d}".format(step)),
+                             128 if step == 0 else 256)
+        index["embed"].append((k, k + 1, k + 2))
+        plan, us = unet_specs(getattr(model, "propagation_{:02d}".format(step)))
+        index["unet"].append((plan, list(range(len(specs), len(specs) + len(us)))))
+        specs += us
+    k = len(specs)
+    k2 = model.kernel_regressor.prediction.out_channels
+    specs += chain_specs(model.kernel_regressor, 256, (k2 + 127) // 128 * 128)
+    index["reg"] = (k, k + 1, k + 2)
+    cached = model.__dict__.get("_sbmc_b200_bank")
+    if cached is None or not cached[0].matches(specs):
+        cached = (WeightBank(specs), index)
+        model.__dict__["_sbmc_b200_bank"] = cached
+    return cached[0], index
 
 
 # -- per-sample 1x1 chains ----------------------------------------------------------------
-def _chain_backward(dy, x, ctx_rows, h1, h2, w1, w2, w3, act, n_img, spp, need_dx, need_dctx,
+def _chain_backward(dy, x, ctx_rows, h1, h2, bank, ks, act, n_img, spp, need_dx, need_dctx,
                     cin_valid, cout_valid=0):
     """Backward of y = W3 a(W2 a(W1 [x | ctx] + b1) + b2) + b3 given dy (bf16 rows, channels
-    padded to a multiple of 128).  Returns (dx, dctx, dw1, db1, dw2, db2, dw3, db3)."""
+    padded to a multiple of 128).  Weight gradients go into the bank's dW buffers.  Returns
+    (dx, dctx, dw1, db1, dw2, db2, dw3, db3)."""
+    k1, k2, k3 = ks
     ca = x.shape[1]
     cb = 0 if ctx_rows is None else ctx_rows.shape[1]
-    w1b, w2b, w3b = _bf(w1), _bf(w2), _bf(w3)
-    if w3b.shape[0] != dy.shape[1]:                     # regressor: 441 rows padded to 512
-        w3b = th.nn.functional.pad(w3b, (0, 0, 0, dy.shape[1] - w3b.shape[0]))
-    dw3, db3 = T.wgrad(dy, h2, cout_valid=cout_valid)
-    dh2 = T.linear(dy, w3b.t().contiguous(), mask=h2, mask_act=act)
-    dw2, db2 = T.wgrad(dh2, h1)
-    dh1 = T.linear(dh2, w2b.t().contiguous(), mask=h1, mask_act=act)
-    dw1 = th.empty(128, cin_valid + cb, device=dy.device, dtype=th.float32)
+    dw3, db3 = T.wgrad(dy, h2, dw=bank.dw(k3), cout_valid=cout_valid)
+    dh2 = T.linear(dy, bank.dgrad(k3), mask=h2, mask_act=act)
+    dw2, db2 = T.wgrad(dh2, h1, dw=bank.dw(k2))
+    dh1 = T.linear(dh2, bank.dgrad(k2), mask=h1, mask_act=act)
+    dw1 = bank.dw(k1)
     _, db1 = T.wgrad(dh1, x, dw=dw1[:, :cin_valid], cin_valid=cin_valid)
+    d1 = bank.dgrad(k1)                                # [cin_pad, 128]: x's rows, then ctx's
     dx = dctx = None
     if need_dx:
-        dx = T.linear(dh1, w1b[:, :ca].t().contiguous())
+        dx = T.linear(dh1, d1[:ca])
     if cb:
         r = T.spp_reduce(dh1, n_img, spp, 1.0)          # sum over the samples of a pixel
         T.wgrad(r, ctx_rows, dw=dw1[:, cin_valid:], want_bias=False)
         if need_dctx:
-            dctx = T.linear(r, w1b[:, ca:].t().contiguous())
+            dctx = T.linear(r, d1[ca:])
     return dx, dctx, dw1, db1, dw2, db2, dw3, db3
 
 
 class EmbedStage(th.autograd.Function):
     """(e, reduced) = embedding chain on the sample rows x [S, ca] (+ pixel rows ctx [P, 128])
-    and its mean over the samples.  w1 fp32 [128, cin_valid + cb] (x's channels first)."""
+    and its mean over the samples.  t1..t3: the bank's tokens of the three convolutions `ks`."""
 
     @staticmethod
-    def forward(ctx, x, ctx_rows, w1, b1, w2, b2, w3, b3, act, n_img, spp, hw):
-        ca = x.shape[1]
-        cin_valid = w1.shape[1] - (0 if ctx_rows is None else ctx_rows.shape[1])
-        w1b = _bf(w1)
-        if cin_valid < ca:                               # x's channels are zero-padded to ca
-            w1b = th.cat([th.nn.functional.pad(w1b[:, :cin_valid], (0, ca - cin_valid)),
-                          w1b[:, cin_valid:]], 1).contiguous()
-        h1 = T.linear(x, w1b, b1.detach().float(), act, xb=ctx_rows, hw=hw, spp=spp)
-        h2 = T.linear(h1, _bf(w2), b2.detach().float(), act)
-        e = T.linear(h2, _bf(w3), b3.detach().float(), 0)
+    def forward(ctx, x, ctx_rows, t1, b1, t2, b2, t3, b3, bank, ks, act, n_img, spp, hw):
+        cb = 0 if ctx_rows is None else ctx_rows.shape[1]
+        h1 = T.linear(x, bank.fwd(ks[0]), b1.detach(), act, xb=ctx_rows, hw=hw, spp=spp)
+        h2 = T.linear(h1, bank.fwd(ks[1]), b2.detach(), act)
+        e = T.linear(h2, bank.fwd(ks[2]), b3.detach(), 0)
         reduced = T.spp_reduce(e, n_img, spp, 1.0 / spp)
-        ctx.save_for_backward(x, ctx_rows, h1, h2, w1b, w2, w3)
-        ctx.cfg = (act, n_img, spp, cin_valid)
+        ctx.save_for_backward(x, ctx_rows, h1, h2)
+        ctx.cfg = (bank, ks, act, n_img, spp, t1.shape[1] - cb)
         return e, reduced
 
     @staticmethod
     def backward(ctx, de, dreduced):
-        x, ctx_rows, h1, h2, w1b, w2, w3 = ctx.saved_tensors
-        act, n_img, spp, cin_valid = ctx.cfg
+        x, ctx_rows, h1, h2 = ctx.saved_tensors
+        bank, ks, act, n_img, spp, cin_valid = ctx.cfg
         if dreduced is not None:
             de = T.bcast_add(None if de is None else de.contiguous(), dreduced.contiguous(),
                              n_img, spp, 1.0 / spp)
@@ -134,8 +147,8 @@ class EmbedStage(th.autograd.Function):
             de = de.contiguous()
         need = ctx.needs_input_grad
         dx, dctx, dw1, db1, dw2, db2, dw3, db3 = _chain_backward(
-            de, x, ctx_rows, h1, h2, w1b, w2, w3, act, n_img, spp, need[0], need[1], cin_valid)
-        return dx, dctx, dw1, db1, dw2, db2, dw3, db3, None, None, None, None
+            de, x, ctx_rows, h1, h2, bank, ks, act, n_img, spp, need[0], need[1], cin_valid)
+        return (dx, dctx, dw1, db1, dw2, db2, dw3, db3) + (None,) * 6
 
 
 class RegressStage(th.autograd.Function):
@@ -143,24 +156,24 @@ class RegressStage(th.autograd.Function):
     [spp, bs, k2, hw] buffer) from the sample rows e [S, 128] and pixel rows ctx [P, 128]."""
 
     @staticmethod
-    def forward(ctx, e, ctx_rows, w1, b1, w2, b2, w3, b3, act, n_img, spp, hw):
-        k2 = w3.shape[0]
-        k2p = (k2 + 127) // 128 * 128
-        h1 = T.linear(e, _bf(w1), b1.detach().float(), act, xb=ctx_rows, hw=hw, spp=spp)
-        h2 = T.linear(h1, _bf(w2), b2.detach().float(), act)
-        w3p = th.nn.functional.pad(_bf(w3), (0, 0, 0, k2p - k2))
-        b3p = th.nn.functional.pad(b3.detach().float(), (0, k2p - k2))
+    def forward(ctx, e, ctx_rows, t1, b1, t2, b2, t3, b3, bank, ks, act, n_img, spp, hw):
+        k2 = t3.shape[0]
+        w3 = bank.fwd(ks[2])                            # [k2 padded, 128], zero rows past k2
+        k2p = w3.shape[0]
+        h1 = T.linear(e, bank.fwd(ks[0]), b1.detach(), act, xb=ctx_rows, hw=hw, spp=spp)
+        h2 = T.linear(h1, bank.fwd(ks[1]), b2.detach(), act)
+        b3p = th.nn.functional.pad(b3.detach(), (0, k2p - k2))
         logits = th.empty(spp, n_img, k2, hw, device=e.device, dtype=th.float32)
-        T.linear(h2, w3p, b3p, 0, hw=hw, spp=spp, out_mode=2, out=logits,
+        T.linear(h2, w3, b3p, 0, hw=hw, spp=spp, out_mode=2, out=logits,
                  out_img_stride=k2 * hw, out_smp_stride=n_img * k2 * hw, cout_valid=k2)
-        ctx.save_for_backward(e, ctx_rows, h1, h2, w1, w2, w3)
-        ctx.cfg = (act, n_img, spp, hw, k2, k2p)
+        ctx.save_for_backward(e, ctx_rows, h1, h2)
+        ctx.cfg = (bank, ks, act, n_img, spp, hw, k2, k2p)
         return tuple(logits[s] for s in range(spp))
 
     @staticmethod
     def backward(ctx, *dlogits):
-        e, ctx_rows, h1, h2, w1, w2, w3 = ctx.saved_tensors
-        act, n_img, spp, hw, k2, k2p = ctx.cfg
+        e, ctx_rows, h1, h2 = ctx.saved_tensors
+        bank, ks, act, n_img, spp, hw, k2, k2p = ctx.cfg
         dy = th.empty(n_img, spp, hw, k2p, device=e.device, dtype=BF)
         for s, g in enumerate(dlogits):
             if g is None:
@@ -170,9 +183,21 @@ class RegressStage(th.autograd.Function):
                                  out_img_stride=spp * hw * k2p)
         need = ctx.needs_input_grad
         dx, dctx, dw1, db1, dw2, db2, dw3, db3 = _chain_backward(
-            dy.view(n_img * spp * hw, k2p), e, ctx_rows, h1, h2, w1, w2, w3, act, n_img, spp,
+            dy.view(n_img * spp * hw, k2p), e, ctx_rows, h1, h2, bank, ks, act, n_img, spp,
             need[0], need[1], e.shape[1], cout_valid=k2)
-        return dx, dctx, dw1, db1, dw2, db2, dw3, db3, None, None, None, None
+        return (dx, dctx, dw1, db1, dw2, db2, dw3, db3) + (None,) * 6
+
+
+def embed_stage(bank, ks, toks, chain, x, ctx_rows, n_img, spp, hw):
+    c1, c2, c3 = _chain_convs(chain)
+    return EmbedStage.apply(x, ctx_rows, toks[ks[0]], c1.bias, toks[ks[1]], c2.bias,
+                            toks[ks[2]], c3.bias, bank, ks, _chain_act(chain), n_img, spp, hw)
+
+
+def regress_stage(bank, ks, toks, chain, e, ctx_rows, n_img, spp, hw):
+    c1, c2, c3 = _chain_convs(chain)
+    return RegressStage.apply(e, ctx_rows, toks[ks[0]], c1.bias, toks[ks[1]], c2.bias,
+                              toks[ks[2]], c3.bias, bank, ks, _chain_act(chain), n_img, spp, hw)
 
 
 # -- U-net ---------------------------------------------------------------------------------
@@ -186,18 +211,6 @@ def _unet_plan(autoencoder):
         right = None if lvl.is_last else _chain_layers(lvl.right)
         plan.append((left, right))
     return plan
-
-
-def _w9(w):
-    """[cout, cin, 3, 3] -> bf16 [9, cout, cin], tap = 3 dy + dx."""
-    cout, cin = w.shape[:2]
-    return w.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(BF).contiguous()
-
-
-def _w9_dgrad(w):
-    """Weights of the data-gradient convolution: [9, cin, cout], taps flipped."""
-    cout, cin = w.shape[:2]
-    return w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, cin, cout).to(BF).contiguous()
 
 
 def _maxpool(x):
@@ -227,23 +240,25 @@ def _upsample_concat(coarse, skip):
 OWN_WGRAD3X3 = True      # False: cuDNN's bf16 weight-gradient kernel (A/B comparisons)
 
 
-def _conv_wgrad(dpre, x, cout, cin):
-    """fp32 [cout, cin, 3, 3] weight gradient of a 3x3 convolution from bf16 rows: the
-    split-K tcgen05 kernel of csrc/wgrad.cu (fp32 output)."""
-    if OWN_WGRAD3X3 and cout % 128 == 0 and cin % 128 == 0:
-        return T.wgrad3x3(dpre, x).view(3, 3, cout, cin).permute(2, 3, 0, 1)
+def _conv_wgrad(dpre, x, dst):
+    """(dW, db) of a 3x3 convolution, dW into dst (fp32 [9, cout, cin]): the split-K tcgen05
+    kernel of csrc/wgrad.cu (the bias gradient comes out of the same launch)."""
+    _, cout, cin = dst.shape
+    if OWN_WGRAD3X3:
+        return T.wgrad3x3(dpre, x, out=dst, want_bias=True)
     dw = th.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (cout, cin, 3, 3),
                                   dpre.permute(0, 3, 1, 2), padding=1)
-    return dw.float()
+    dst.copy_(dw.permute(2, 3, 0, 1).reshape(9, cout, cin))
+    return dst, T.colsum(dpre.view(-1, cout))
 
 
 class UNetStage(th.autograd.Function):
-    """y = Autoencoder(x) on bf16 [n, h, w, c] tensors.  `params` = effective fp32 weight
-    [cout, cin, 3, 3] and bias of every convolution in `plan` order (level by level, left
-    then right)."""
+    """y = Autoencoder(x) on bf16 [n, h, w, c] tensors.  `params` = (bank token, bias) of
+    every convolution in `plan` order (level by level, left then right); ks: their bank
+    indices."""
 
     @staticmethod
-    def forward(ctx, x, plan, *params):
+    def forward(ctx, x, plan, bank, ks, *params):
         tape = []            # one record per level, finest first
 
         # parameters come level by level, left then right; the recursion visits left(k),
@@ -260,7 +275,7 @@ class UNetStage(th.autograd.Function):
             recs = []
             for j, (_, act) in enumerate(layers):
                 i = start + 2 * j
-                y = T.conv3x3(a, _w9(params[i]), params[i + 1].detach().float().contiguous(), act)
+                y = T.conv3x3(a, bank.fwd(ks[i // 2]), params[i + 1].detach(), act)
                 recs.append((i, a, y, act))
                 a = y
             return a, recs
@@ -280,13 +295,13 @@ class UNetStage(th.autograd.Function):
 
         y = level(0, x.contiguous())
         ctx.tape = tape
-        ctx.params = params
+        ctx.bank, ctx.ks = bank, ks
         ctx.nparams = len(params)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        tape, params = ctx.tape, ctx.params
+        tape, bank, ks = ctx.tape, ctx.bank, ctx.ks
         grads = [None] * ctx.nparams
         zeros = {}
 
@@ -300,17 +315,17 @@ class UNetStage(th.autograd.Function):
             gradient w.r.t. the chain's input (no activation derivative applied)."""
             for j in range(len(recs) - 1, -1, -1):
                 i, a, y, act = recs[j]
-                w = params[i]
-                cout, cin = w.shape[:2]
-                grads[i] = _conv_wgrad(dpre, a, cout, cin)
-                grads[i + 1] = T.colsum(dpre.view(-1, cout))
+                k = ks[i // 2]
+                wd = bank.dgrad(k)                           # [9, cin, cout]
+                cin, cout = wd.shape[1], wd.shape[2]
+                grads[i], grads[i + 1] = _conv_wgrad(dpre, a, bank.dw(k))
                 if j > 0:
                     # the input of this conv is the activated output of the previous one:
                     # its derivative goes into the epilogue
-                    dpre = T.conv3x3(dpre, _w9_dgrad(w), zero_bias(cin, dpre.device), 0,
+                    dpre = T.conv3x3(dpre, wd, zero_bias(cin, dpre.device), 0,
                                      mask=a, mask_act=recs[j - 1][3])
                 else:
-                    dpre = T.conv3x3(dpre, _w9_dgrad(w), zero_bias(cin, dpre.device), 0)
+                    dpre = T.conv3x3(dpre, wd, zero_bias(cin, dpre.device), 0)
             return dpre
 
         def level_bwd(k, dpre):
@@ -333,22 +348,17 @@ class UNetStage(th.autograd.Function):
         dpre = T.dact(last[2], dy.contiguous(), last[3]) if last[3] else dy.contiguous()
         dx = level_bwd(0, dpre)
         ctx.tape = None
-        return (dx, None) + tuple(grads)
+        return (dx, None, None, None) + tuple(grads)
 
 
-def _unet_params(autoencoder, plan):
-    out = []
-    for left, right in plan:
-        for conv, _ in left + (right or []):
-            out.append(_eff_weight(conv))
-            out.append(conv.bias)
-    return out
-
-
-def unet_forward(autoencoder, x):
+def unet_stage(bank, plan, ks, toks, x):
     """Differentiable bf16 forward of `modules.Autoencoder` on x [n, h, w, c] bf16."""
-    plan = _unet_plan(autoencoder)
-    return UNetStage.apply(x, plan, *_unet_params(autoencoder, plan))
+    params = []
+    convs = [conv for left, right in plan for conv, _ in left + (right or [])]
+    for k, conv in zip(ks, convs):
+        params.append(toks[k])
+        params.append(conv.bias)
+    return UNetStage.apply(x, plan, bank, ks, *params)
 
 
 # -- the model --------------------------------------------------------------------------
@@ -362,8 +372,13 @@ def supported(model, nf, ngf, h, w):
     chains = [getattr(model, "embedding_{:02d}".format(i)) for i in range(model.nsteps)]
     if not all(conv1x1.supports(c) for c in chains + [model.kernel_regressor]):
         return False
-    return all(unet_fast.supports_training(getattr(model, "propagation_{:02d}".format(i)))
-               for i in range(model.nsteps))
+    if not all(unet_fast.supports_training(getattr(model, "propagation_{:02d}".format(i)))
+               for i in range(model.nsteps)):
+        return False
+    # the weight bank normalizes every convolution itself
+    return all(hasattr(m, "weight_v") and hasattr(m, "weight_g") and m.weight_v.is_cuda
+               and m.weight_v.dtype == th.float32
+               for m in model.modules() if isinstance(m, th.nn.Conv2d))
 
 
 def forward_train(model, radiance, features, gfeatures):
@@ -378,17 +393,16 @@ def forward_train(model, radiance, features, gfeatures):
     gidx = th.arange(bs * spp, device=feats.device) % bs
     x[:, :, nf:nf + ngf] = gfeatures.reshape(bs, ngf)[gidx].unsqueeze(1).to(BF)
     x = x.view(bs * spp * hw, 128)
+    bank, index = _model_bank(model, nf, ngf)
+    toks = bank.apply()                      # one launch: every bf16 operand of the step
     prop = None
     for step in range(model.nsteps):
         embed = getattr(model, "embedding_{:02d}".format(step))
-        cin = (nf + ngf) if step == 0 else 256
-        w1, b1, w2, b2, w3, b3, act = _chain_params(embed, cin)
-        x, reduced = EmbedStage.apply(x, prop, w1, b1, w2, b2, w3, b3, act, bs, spp, hw)
-        unet = getattr(model, "propagation_{:02d}".format(step))
-        prop = unet_forward(unet, reduced.view(bs, h, w, 128)).view(bs * hw, 128)
-    w1, b1, w2, b2, w3, b3, act = _chain_params(model.kernel_regressor, 256)
-    logits = RegressStage.apply(x, prop, w1, b1, w2, b2, w3, b3, act, bs, spp, hw)
-    k2 = w3.shape[0]
+        x, reduced = embed_stage(bank, index["embed"][step], toks, embed, x, prop, bs, spp, hw)
+        plan, ks = index["unet"][step]
+        prop = unet_stage(bank, plan, ks, toks, reduced.view(bs, h, w, 128)).view(bs * hw, 128)
+    logits = regress_stage(bank, index["reg"], toks, model.kernel_regressor, x, prop, bs, spp, hw)
+    k2 = logits[0].shape[1]
     sum_r = sum_w = max_w = None
     for sp in range(spp):
         kernels = logits[sp].view(bs, k2, h, w)

@@ -35,6 +35,7 @@ int main(void) {
       (entry_fn)sbmc_linear2_nhwc_bf16,
       (entry_fn)sbmc_wgrad_nhwc_bf16,
       (entry_fn)sbmc_wgrad3x3_nhwc_bf16,
+      (entry_fn)sbmc_weight_bank_run,
       (entry_fn)sbmc_conv3x3_masked_nhwc_bf16,
       (entry_fn)sbmc_spp_reduce_nhwc_bf16,
       (entry_fn)sbmc_bcast_add_nhwc_bf16,

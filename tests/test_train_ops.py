@@ -201,7 +201,8 @@ def test_wgrad3x3_matches_conv2d_weight(n, h, w, cout, cin):
     th.manual_seed(n * h + w)
     dp = th.randn(n, h, w, cout, device="cuda").to(BF)
     x = th.randn(n, h, w, cin, device="cuda").to(BF)
-    got = T.wgrad3x3(dp, x)
+    got, db = T.wgrad3x3(dp, x, want_bias=True)
+    assert rel(db, dp.double().sum((0, 1, 2))) < 1e-5
     ref = th.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (cout, cin, 3, 3),
                                    dp.double().permute(0, 3, 1, 2), padding=1)
     ref9 = ref.permute(2, 3, 0, 1).reshape(9, cout, cin)

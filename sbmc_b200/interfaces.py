@@ -101,6 +101,8 @@ class SampleBasedDenoiserInterface(object):
 
     def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False, allow_tf32=False,
                  cuda_graph=False):
+        if cuda_graph and not (cuda and fused_optimizer):
+            raise ValueError("cuda_graph needs cuda=True and fused_optimizer=True")
         self.allow_tf32 = bool(allow_tf32)
         th.backends.cudnn.allow_tf32 = self.allow_tf32
         th.backends.cuda.matmul.allow_tf32 = self.allow_tf32
@@ -116,8 +118,6 @@ class SampleBasedDenoiserInterface(object):
         # hundred small launches: without the graph the host, not the GPU, sets its pace)
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
-        if self.cuda_graph and not (cuda and fused_optimizer):
-            raise ValueError("cuda_graph needs cuda=True and fused_optimizer=True")
         self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:
             from .optim import FusedAdam

@@ -288,3 +288,27 @@ def test_kpcn_mode_scripts(tmp_path, backend):
     finally:
         for p_ in patches:
             p_.stop()
+
+
+@pytest.mark.gpu
+def test_train_script_mixed_precision_pipeline_under_a_cuda_graph(tmp_path):
+    """scripts/train.py --bf16_train --cuda_graph: the tcgen05 training pipeline
+    (sbmc_b200/train_pipeline.py) replayed from one CUDA graph per batch shape, from the
+    .bin tiles to the checkpoint; the denoise script then loads what it wrote."""
+    import torch as th
+    root = _scene(tmp_path)
+    train = load_script("train")
+    denoise = load_script("denoise")
+    ckpt = str(tmp_path / "ckpt")
+    train.main(train.parser().parse_args(
+        ["--data", root, "--checkpoint_dir", ckpt, "--constant_spp", "--spp", "2", "--bs", "3",
+         "--ksize", "3", "--num_epochs", "2", "--max_steps", "5", "--log_every", "1",
+         "--bf16_train", "--cuda_graph"]))
+    state = th.load(os.path.join(ckpt, "training_end.pth"), map_location="cpu", weights_only=False)
+    tensors = [v for v in state["model"].values() if isinstance(v, th.Tensor)]
+    assert tensors and all(th.isfinite(v).all() for v in tensors)
+    out = str(tmp_path / "out.exr")
+    denoise.main(denoise.parser().parse_args(
+        ["--input", os.path.join(root, "scene"), "--checkpoint", ckpt, "--output", out]))
+    img = imageio.read_exr(out)
+    assert img.shape == (48, 48, 3) and np.isfinite(img).all()

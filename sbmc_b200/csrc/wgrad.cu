@@ -517,7 +517,7 @@ extern "C" int sbmc_wgrad3x3_nhwc_bf16(const void *dp, const void *x, int64_t n,
   SBMC_CUDA_OK(cudaGetLastError());
   // partial is [nsplit][9 * cout][cin]
   const long long total = 9ll * cout * cin;
-  if (nsplit <= 24) {
+  if (nsplit <= 64) {
     const long long total4 = total / 4;
     const long long b = (total4 + 255) / 256;
     wg::wgrad_reduce_vec_kernel<<<(unsigned)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(

@@ -10,7 +10,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'wgr
   -o gpurun_out/${tag}_train_prof python benchmarks/train_kernels_bench.py --ncu > gpurun_out/${tag}_ncu.log 2>&1
 tail -1 gpurun_out/${tag}_ncu.log
 echo "== launch list of one eager step"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv \
   python - > gpurun_out/${tag}_launch.log 2>&1 <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -26,19 +26,24 @@ batch = {"radiance": th.rand(8, 8, 3, 128, 128, device=dev), "features": th.rand
 for _ in range(2):
     iface.train_step(batch)
 th.cuda.synchronize()
+th.cuda.profiler.start()
+iface.train_step(batch)
+th.cuda.synchronize()
+th.cuda.profiler.stop()
 PY
 python - <<'PY'
 import csv, collections, os
 tag = os.environ.get("TAG", "r3c")
 rows = [r for r in csv.reader(open("gpurun_out/%s_launches.csv" % tag)) if len(r) > 10 and r[0].isdigit()]
-half = rows[len(rows) // 2:]                      # the second (warm) step
+half = rows                                       # cudaProfilerStart/Stop bracket one warm step
 agg = collections.OrderedDict()
 for r in half:
     name = r[4].split("(")[0].replace("void ", "")[:70]
     t = float(r[-1].replace(",", ""))
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += t
 tot = sum(a[1] for a in agg.values())
-repo = sum(a[1] for k, a in agg.items() if "sbmc" in k)
+repo = sum(a[1] for k, a in agg.items()
+           if k.startswith(("sbmc::", "lin::", "c3::", "wg::", "tr::", "wb::")))
 with open("gpurun_out/%s_step_launch_list.txt" % tag, "w") as f:
     f.write("one config-4 training step (bf16 pipeline, eager), ncu gpu__time_duration per kernel (serialised, cold)\n")
     f.write("%d launches, %.2f ms of kernel time; repo kernels: %.1f %% of it\n" % (len(half), tot / 1e6, 100 * repo / tot))

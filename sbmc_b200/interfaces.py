@@ -53,6 +53,7 @@ class _GraphedStep(object):
                         old = saved_s.get(p, {}).get(k)
                         v.zero_() if old is None else v.copy_(old)
         del saved_p, saved_s
+        self.generation = getattr(opt, "generation", 0)
         self.graph = th.cuda.CUDAGraph()
         with th.cuda.graph(self.graph):
             self._body()
@@ -179,6 +180,9 @@ class SampleBasedDenoiserInterface(object):
         key = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in batch.items()
                            if isinstance(v, th.Tensor)))
         step = self._graphs.get(key)
+        if step is not None and step.generation != getattr(self.optimizer, "generation", 0):
+            self._graphs.clear()          # the optimizer's state tensors were replaced
+            step = None
         if step is None:
             if len(self._graphs) >= 4:
                 self._graphs.clear()

@@ -80,6 +80,16 @@ class FusedAdam(th.optim.Optimizer):
         self.capturable = bool(capturable)
         self._dev_step = None
         self._table_cache = {}          # pointer tuple -> (tensors, chunks, nchunks, partial)
+        self.generation = 0             # bumped when the state tensors are replaced
+
+    def load_state_dict(self, state_dict):
+        """torch replaces every state tensor: device tables and the shared step count are
+        rebuilt on the next step, and anything that captured the old addresses (a CUDA graph
+        of the training step) must be rebuilt too -- `generation` tells it."""
+        super(FusedAdam, self).load_state_dict(state_dict)
+        self._table_cache.clear()
+        self._dev_step = None
+        self.generation += 1
 
     def _cached_tables(self, rows, dev, backend):
         key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())

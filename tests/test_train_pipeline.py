@@ -227,3 +227,40 @@ def test_cuda_graph_step_follows_the_eager_step(bf16):
     assert (num / den).sqrt().item() < 1e-4
     assert float(graph.optimizer.state[next(graph.model.parameters())]["step"]) == 3.0
     assert len(graph._graphs) == 1
+
+
+def test_cuda_graph_step_survives_an_optimizer_state_reload():
+    """Checkpoint / resume under cuda_graph: loading an optimizer state dict replaces the
+    state tensors, the captured step is rebuilt and training continues where the
+    uninterrupted run goes."""
+    from sbmc_b200 import interfaces
+
+    def make():
+        th.manual_seed(2)
+        net = models.Multisteps(12, 3, ksize=5, nsteps=1).cuda().train()
+        net.bf16_train = True
+        return interfaces.SampleBasedDenoiserInterface(net, lr=1e-3, cuda=True, fused_optimizer=True,
+                                                       cuda_graph=True)
+    bs, spp, h, w = 2, 2, 16, 16
+    g = th.Generator(device="cuda").manual_seed(9)
+    batches = [{"radiance": th.rand(bs, spp, 3, h, w, device="cuda", generator=g),
+                "features": th.randn(bs, spp, 12, h, w, device="cuda", generator=g),
+                "global_features": th.randn(bs, 3, 1, 1, device="cuda", generator=g),
+                "target_image": th.rand(bs, 3, h, w, device="cuda", generator=g)}
+               for _ in range(4)]
+    straight = make()
+    for b in batches:
+        straight.train_step(dict(b))
+    first = make()
+    for b in batches[:2]:
+        first.train_step(dict(b))
+    resumed = make()
+    resumed.train_step(dict(batches[0]))                     # a graph exists before the reload
+    resumed.model.load_state_dict(first.model.state_dict())
+    resumed.optimizer.load_state_dict(first.optimizer.state_dict())
+    for b in batches[2:]:
+        resumed.train_step(dict(b))
+    assert float(resumed.optimizer.state[next(resumed.model.parameters())]["step"]) == 4.0
+    num = sum(((q - p) ** 2).sum() for p, q in zip(straight.model.parameters(), resumed.model.parameters()))
+    den = sum((p ** 2).sum() for p in straight.model.parameters())
+    assert (num / den).sqrt().item() < 1e-4

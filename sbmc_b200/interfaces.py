@@ -55,7 +55,9 @@ class _GraphedStep(object):
         del saved_p, saved_s
         self.generation = getattr(opt, "generation", 0)
         self.graph = th.cuda.CUDAGraph()
-        with th.cuda.graph(self.graph):
+        # thread_local: other threads (the PrefetchLoader's reader, NCCL's watchdog) may issue
+        # CUDA calls while this thread captures
+        with th.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._body()
         LOG.info("training step captured in a CUDA graph (%s)",
                  ", ".join("%s %s" % (k, tuple(v.shape)) for k, v in self.static.items()

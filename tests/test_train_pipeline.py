@@ -264,3 +264,32 @@ def test_cuda_graph_step_survives_an_optimizer_state_reload():
     num = sum(((q - p) ** 2).sum() for p, q in zip(straight.model.parameters(), resumed.model.parameters()))
     den = sum((p ** 2).sum() for p in straight.model.parameters())
     assert (num / den).sqrt().item() < 1e-4
+
+
+def test_training_curves_of_the_pipeline_and_the_fp32_path_agree():
+    """40 Adam steps on a fixed set of batches: the mixed-precision pipeline (one CUDA graph)
+    and the reference-arithmetic fp32 path start from the same weights, both reduce the
+    loss, and their loss curves stay within a few percent of each other."""
+    from sbmc_b200 import interfaces
+    bs, spp, h, w = 2, 2, 32, 32
+    g = th.Generator(device="cuda").manual_seed(11)
+    target = th.rand(bs, 3, h, w, device="cuda", generator=g)
+    batches = []
+    for _ in range(4):
+        rad = target.unsqueeze(1) + 0.3 * th.randn(bs, spp, 3, h, w, device="cuda", generator=g)
+        batches.append({"radiance": rad.clamp_min(0),
+                        "features": th.cat([rad, th.randn(bs, spp, 9, h, w, device="cuda", generator=g)], 2),
+                        "global_features": th.randn(bs, 3, 1, 1, device="cuda", generator=g),
+                        "target_image": target})
+    curves = {}
+    for name, bf16, graph in (("fp32", False, False), ("pipeline", True, True)):
+        th.manual_seed(3)
+        net = models.Multisteps(12, 3, ksize=5, nsteps=2).cuda().train()
+        net.bf16_train = bf16
+        iface = interfaces.SampleBasedDenoiserInterface(net, lr=3e-4, cuda=True, fused_optimizer=True,
+                                                        cuda_graph=graph)
+        curves[name] = [iface.train_step(dict(batches[i % 4]))[1]["loss"] for i in range(40)]
+    a, b = th.tensor(curves["fp32"]), th.tensor(curves["pipeline"])
+    assert a[-4:].mean() < 0.8 * a[:4].mean() and b[-4:].mean() < 0.8 * b[:4].mean()
+    assert ((a - b).abs() / a).max().item() < 0.1
+    assert ((a[-8:] - b[-8:]).abs() / a[-8:]).mean().item() < 0.05

@@ -31,7 +31,7 @@ class _GraphedStep(object):
                        for k, v in batch.items()}
         self.params = [p for p in iface.model.parameters() if p.requires_grad]
         for p in self.params:
-            if p.grad is None:
+            if p.grad is None:                  # (distributed: already views of the flat buffer)
                 p.grad = th.zeros_like(p, memory_format=th.contiguous_format)
         opt = iface.optimizer
         saved_p = [p.detach().clone() for p in self.params]
@@ -65,10 +65,14 @@ class _GraphedStep(object):
 
     def _body(self):
         iface = self.iface
-        th._foreach_zero_([p.grad for p in self.params])
+        if iface.distributed:
+            iface._flat_grad.zero_()
+        else:
+            th._foreach_zero_([p.grad for p in self.params])
         fwd = iface.model(self.static)
         loss, out, tgt = iface._scores(self.static, fwd)
         loss.backward()
+        iface._average_grads()                  # NCCL all-reduce: a node of the captured graph
         iface.optimizer.step(max_norm=_GRAD_CLIP)
         with th.no_grad():
             self.scalars = th.stack([loss.detach().float().reshape(()),
@@ -103,7 +107,7 @@ class SampleBasedDenoiserInterface(object):
     logged."""
 
     def __init__(self, model, lr=1e-4, cuda=False, fused_optimizer=False, allow_tf32=False,
-                 cuda_graph=False):
+                 cuda_graph=False, distributed=False):
         if cuda_graph and not (cuda and fused_optimizer):
             raise ValueError("cuda_graph needs cuda=True and fused_optimizer=True")
         self.allow_tf32 = bool(allow_tf32)
@@ -128,6 +132,45 @@ class SampleBasedDenoiserInterface(object):
                                        capturable=self.cuda_graph)
         else:
             self.optimizer = th.optim.Adam(self.model.parameters(), lr=lr)
+        # distributed (extra): data-parallel training over torch.distributed (one process
+        # per GPU, NCCL; gloo on CPU in the tests).  The reference is single-device.  Every
+        # rank trains on its own batches; after backward the gradients -- views of ONE flat
+        # fp32 buffer -- are averaged with one all-reduce, before clipping and Adam.
+        self.distributed = bool(distributed)
+        self._flat_grad = None
+        if self.distributed:
+            self._setup_distributed()
+
+    def _setup_distributed(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("distributed=True needs an initialised torch.distributed group")
+        self._dist = dist
+        self.world = dist.get_world_size()
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        with th.no_grad():
+            for p in params:                          # same starting point on every rank
+                dist.broadcast(p.data, 0)
+        self._flat_grad = th.zeros(sum(p.numel() for p in params), dtype=th.float32,
+                                   device=params[0].device)
+        off = 0
+        for p in params:
+            if p.dtype != th.float32 or not p.is_contiguous():
+                raise RuntimeError("distributed training wants contiguous float32 parameters")
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _zero_grads(self):
+        if self.distributed:
+            self._flat_grad.zero_()                   # the gradients stay views of the buffer
+        else:
+            self.optimizer.zero_grad()
+
+    def _average_grads(self):
+        """One all-reduce over the flat gradient buffer, then the mean."""
+        if self.distributed and self.world > 1:
+            self._dist.all_reduce(self._flat_grad)
+            self._flat_grad.mul_(1.0 / self.world)
 
     # -- helpers -----------------------------------------------------------------
     def _to_device(self, batch):
@@ -148,9 +191,10 @@ class SampleBasedDenoiserInterface(object):
         return self.model(self._to_device(batch))
 
     def backward(self, batch, fwd):
-        self.optimizer.zero_grad()
+        self._zero_grads()
         loss, out, tgt = self._scores(batch, fwd)
         loss.backward()
+        self._average_grads()
         value = loss.item()
         if not math.isfinite(value):      # outliers in the data show up here
             kind = "NaN" if math.isnan(value) else "Infinite"
@@ -190,6 +234,19 @@ class SampleBasedDenoiserInterface(object):
                 self._graphs.clear()
             step = self._graphs[key] = _GraphedStep(self, batch)
         return step.run(batch)
+
+    def close(self):
+        """Drop the captured graphs (and the NCCL nodes inside them) before the process
+        group is destroyed / the process exits: a live graph that references the
+        communicator can stall the teardown."""
+        import gc
+        for step in self._graphs.values():
+            step.graph = None
+            step.iface = None
+        self._graphs.clear()
+        gc.collect()
+        if self.device == "cuda":
+            th.cuda.synchronize()
 
     def init_validation(self):
         return {"loss": 0.0, "rmse": 0.0, "n": 0}

@@ -31,10 +31,22 @@ def _device():
     return "cuda"
 
 
+def _init_distributed():
+    """(rank, world) under torchrun (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* in the
+    environment): one process per GPU over NCCL."""
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    th.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    return rank, world
+
+
 def main(args):
     np.random.seed(0)
     th.manual_seed(0)
     device = _device()
+    rank, world = _init_distributed() if args.distributed else (0, 1)
     data_args = dict(spp=args.spp,
                      mode=datasets.TilesDataset.KPCN_MODE if args.kpcn_mode
                      else datasets.TilesDataset.SBMC_MODE,
@@ -74,20 +86,27 @@ def main(args):
         model.bf16_train = True        # mixed-precision pipeline on the repo's tcgen05 kernels
     interface = interfaces.SampleBasedDenoiserInterface(
         model, lr=args.lr, cuda=device == "cuda",
-        fused_optimizer=args.fused_optimizer or args.cuda_graph, cuda_graph=args.cuda_graph)
+        fused_optimizer=args.fused_optimizer or args.cuda_graph, cuda_graph=args.cuda_graph,
+        distributed=world > 1)
     checkpointer = _compat.Checkpointer(args.checkpoint_dir, model, meta=meta,
                                         optimizers=interface.optimizer)
     checkpointer.load_latest()
 
     trainer = _compat.Trainer(interface)
-    trainer.add_callback(_compat.LoggingCallback(["loss", "rmse"], frequency=args.log_every))
-    trainer.add_callback(_compat.CheckpointingCallback(checkpointer))
-    if args.display_every > 0:      # the reference shows this gallery in Visdom (train.py:116-118)
+    if rank == 0:                   # one rank logs and writes checkpoints (all hold the same weights)
+        trainer.add_callback(_compat.LoggingCallback(["loss", "rmse"], frequency=args.log_every))
+        trainer.add_callback(_compat.CheckpointingCallback(checkpointer))
+    if args.display_every > 0 and rank == 0:      # the reference shows this gallery in Visdom (train.py:116-118)
         trainer.add_callback(callbacks.DenoisingDisplayCallback(
             frequency=args.display_every, out_dir=os.path.join(args.checkpoint_dir, "display")))
     LOG.info("Training started, 'Ctrl+C' to abort.")
     trainer.train(loader, num_epochs=args.num_epochs, val_dataloader=val_loader,
                   max_steps=args.max_steps)
+    interface.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def parser():
@@ -119,6 +138,9 @@ def parser():
     p.add_argument("--cuda_graph", action="store_true",
                    help="capture the training step in a CUDA graph per batch shape (extra; "
                         "implies --fused_optimizer; use with --constant_spp).")
+    p.add_argument("--distributed", action="store_true",
+                   help="data-parallel training under torchrun: one process per GPU, gradients "
+                        "averaged with one NCCL all-reduce per step (extra).")
     p.add_argument("--spp", type=int, default=8, help="Max number of samples per pixel.")
     p.add_argument("--kpcn_mode", dest="kpcn_mode", action="store_true", default=False)
     p.add_argument("--gather", dest="gather", action="store_true", default=False)

@@ -742,13 +742,22 @@ class PrefetchLoader(object):
     batch_size = 1 (the sample dimension varies / images are whole).  kpcn mode has
     no split host half and is iterated plainly."""
 
-    def __init__(self, dataset, batch_size=1, shuffle=False, drop_last=False, generator=None):
+    def __init__(self, dataset, batch_size=1, shuffle=False, drop_last=False, generator=None,
+                 device_prefetch=0):
         if batch_size < 1:
             raise ValueError("batch_size must be positive")
         if not isinstance(dataset, TilesDataset) and batch_size != 1:
             raise ValueError("batch_size must be 1 for %s" % type(dataset).__name__)
         self.dataset, self.batch_size = dataset, batch_size
         self.shuffle, self.drop_last, self.generator = shuffle, drop_last, generator
+        # device_prefetch = D > 0 (TilesDataset in sbmc mode on a GPU): D batches at a time
+        # are read, inflated and assembled as ONE group on a side stream by a background
+        # thread while the consumer trains on the previous group.  The inflater decodes one
+        # LZ4 frame per warp and a frame is a serial chain (~0.1 s for a 128 x 128 sample
+        # plane of 27 floats): a single batch of 8 tiles keeps 72 warps busy for that long,
+        # D batches keep 72 D warps busy for the same time -- the per-batch cost drops D-fold
+        # and the decode overlaps the training step (benchmarks/train_e2e_bench.py).
+        self.device_prefetch = int(device_prefetch)
         # while the copy / kernels of one batch read the first buffer, the files of
         # the next batch are read into the second; both belong to this loader only
         self._stagings = (_Staging(), _Staging())
@@ -785,6 +794,95 @@ class PrefetchLoader(object):
             return [d[self._resolve(i)[1]] for i in batch]
         return d.__getitems__([self._resolve(i)[1] for i in batch], planned=planned)
 
+    def _can_prefetch_on_device(self):
+        d = self.dataset
+        parts = d.datasets if isinstance(d, ConcatDataset) else [d]
+        return (len(parts) == 1 and isinstance(parts[0], TilesDataset)
+                and parts[0].mode == TilesDataset.SBMC_MODE)
+
+    def _iter_device_prefetch(self, batches):
+        """Groups of `device_prefetch` batches, each decoded by one pair of launches on a side
+        stream from a background thread; the consumer's stream waits on the group's event."""
+        import contextlib
+        import queue
+        from concurrent.futures import ThreadPoolExecutor
+        from torch.utils.data import default_collate
+        depth = self.device_prefetch
+        groups = [batches[g:g + depth] for g in range(0, len(batches), depth)]
+        d = self.dataset.datasets[0] if isinstance(self.dataset, ConcatDataset) else self.dataset
+        on_gpu = _backend(d.device).device.type == "cuda"     # (host emulation in the tests: no streams)
+        cuda_device = th.cuda.current_device() if on_gpu else None
+        side = th.cuda.Stream(device=cuda_device) if on_gpu else None
+        ready = queue.Queue(maxsize=2)
+        stop = threading.Event()
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    ready.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def worker():
+            try:
+                if on_gpu:
+                    th.cuda.set_device(cuda_device)
+                with ThreadPoolExecutor(max_workers=1, thread_name_prefix="sbmc-plan") as planner, \
+                        (th.cuda.stream(side) if on_gpu else contextlib.nullcontext()):
+                    flat = lambda grp: [i for b in grp for i in b]          # noqa: E731
+                    pending = planner.submit(self._host_half, flat(groups[0]), 0, cuda_device)
+                    for g, grp in enumerate(groups):
+                        if stop.is_set():
+                            return
+                        planned = pending.result()
+                        if g + 1 < len(groups):
+                            pending = planner.submit(self._host_half, flat(groups[g + 1]),
+                                                     (g + 1) % 2, cuda_device)
+                        items = self._device_half(flat(grp), planned)
+                        out, k = [], 0
+                        for b in grp:
+                            out.append(default_collate(items[k:k + len(b)]))
+                            k += len(b)
+                        del items
+                        ev = None
+                        if on_gpu:
+                            ev = th.cuda.Event()
+                            ev.record(side)
+                        if not put((out, ev)):
+                            return
+                put(None)
+            except BaseException as exc:            # surfaces in the consumer
+                put(exc)
+
+        thread = threading.Thread(target=worker, name="sbmc-device-prefetch", daemon=True)
+        thread.start()
+        try:
+            while True:
+                item = ready.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                out, ev = item
+                if on_gpu:
+                    cur = th.cuda.current_stream(cuda_device)
+                    cur.wait_event(ev)
+                    for batch in out:
+                        for v in batch.values():        # allocated on the side stream, used here
+                            if isinstance(v, th.Tensor) and v.is_cuda:
+                                v.record_stream(cur)
+                for batch in out:
+                    yield batch
+        finally:
+            stop.set()
+            while thread.is_alive():
+                try:
+                    ready.get_nowait()
+                except queue.Empty:
+                    thread.join(timeout=0.05)
+
     def __iter__(self):
         from concurrent.futures import ThreadPoolExecutor
         from torch.utils.data import default_collate
@@ -794,6 +892,9 @@ class PrefetchLoader(object):
         if self.drop_last and batches and len(batches[-1]) < self.batch_size:
             batches.pop()
         if not batches:
+            return
+        if self.device_prefetch > 0 and self._can_prefetch_on_device():
+            yield from self._iter_device_prefetch(batches)     # (forwards close() to the worker's owner)
             return
         # one planner thread, distinct from the file-read pool it fans out to
         cuda_device = th.cuda.current_device() if th.cuda.is_available() else None

@@ -138,6 +138,10 @@ def parser():
     p.add_argument("--cuda_graph", action="store_true",
                    help="capture the training step in a CUDA graph per batch shape (extra; "
                         "implies --fused_optimizer; use with --constant_spp).")
+    p.add_argument("--device_prefetch", type=int, default=0,
+                   help="decode this many batches at a time on a side stream while the previous "
+                        "ones train (extra; LZ4 frames are serial chains, one per warp: wide groups "
+                        "keep the inflater off the critical path).")
     p.add_argument("--distributed", action="store_true",
                    help="data-parallel training under torchrun: one process per GPU, gradients "
                         "averaged with one NCCL all-reduce per step (extra).")

@@ -567,6 +567,27 @@ def test_prefetch_loader_equals_the_dataloader(backend):
     assert th.equal(probe["features"], want[2]["features"][1])
 
 
+def test_device_prefetch_yields_the_same_batches(backend):
+    """device_prefetch = D: groups of D batches decoded by one pair of launches on a side
+    stream from a background thread (GPU backend; elsewhere the plain path serves it) --
+    same batches, same order; leaving the loop early stops the worker."""
+    tiles = datasets.TilesDataset(DATA, spp=2)
+    want = list(datasets.PrefetchLoader(tiles, batch_size=2, shuffle=True,
+                                        generator=th.Generator().manual_seed(5)))
+    for depth in (1, 2, 3, 16):
+        got = list(datasets.PrefetchLoader(tiles, batch_size=2, shuffle=True, device_prefetch=depth,
+                                           generator=th.Generator().manual_seed(5)))
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            _same_batch(a, b)
+    it = iter(datasets.PrefetchLoader(tiles, batch_size=1, device_prefetch=2))
+    first = next(it)
+    _same_batch(first, next(iter(datasets.PrefetchLoader(tiles, batch_size=1))))
+    it.close()                          # generator exit: the worker thread is told to stop
+    import threading
+    assert not [t for t in threading.enumerate() if t.name == "sbmc-device-prefetch" and t.is_alive()]
+
+
 def test_corrupt_tile_raises_like_the_reference(tmp_path, backend):
     src = fixture_files(False)[0]
     folder = tmp_path / "scene"

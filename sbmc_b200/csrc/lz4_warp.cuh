@@ -203,13 +203,24 @@ SBMC_LZ4_FN void match_lanes(uint8_t *dst, int64_t offset, int64_t n) {
 
 // One LZ4 block [ip, ip_end) appended at dst + op; `window` = first output byte
 // a match may reference.  Returns a Status; *op_io advances by the block's size.
+//
+// A frame is a serial chain of sequences and ONE warp walks it, so the cost of a frame is
+// (instructions per sequence) x (sequences): ncu of the first version showed the kernel
+// issue-bound per warp, not memory-bound (profiles/r3p_lz4_ncu.md).  Short sequences --
+// at most 32 literals and a match of at most 32 bytes, the common case on sample data,
+// where most matches are one repeated float -- therefore take a loop-free path: one
+// predicated byte per lane for the literals, one for the match, 32-bit lengths, cursors as
+// pointers.  One __syncwarp() per sequence, in front of the match (it publishes the
+// previous match and this sequence's literals to the lanes that may read them).
 SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *dst,
                              int64_t *op_io, int64_t dst_cap, int64_t window) {
-  int64_t op = *op_io;
+  uint8_t *out = dst + *op_io;
+  uint8_t *const out_end = dst + dst_cap;
+  const uint8_t *const win = dst + window;
   for (;;) {
     if (ip >= ip_end) return kTruncated;
     const uint32_t token = *ip++;
-    int64_t lit = token >> 4;
+    uint32_t lit = token >> 4;
     if (lit == 15) {
       uint32_t b;
       do {
@@ -218,16 +229,22 @@ SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *
         lit += b;
       } while (b == 255);
     }
-    if (lit > ip_end - ip) return kTruncated;
-    if (lit > dst_cap - op) return kOverflow;
-    copy_lanes(dst + op, ip, lit);
+    if ((int64_t)lit > ip_end - ip) return kTruncated;
+    if ((int64_t)lit > out_end - out) return kOverflow;
+    if (lit <= 32) {
+      SBMC_LZ4_LANES(lane) {
+        if ((uint32_t)lane < lit) out[lane] = ip[lane];
+      }
+    } else {
+      copy_lanes(out, ip, lit);
+    }
     ip += lit;
-    op += lit;
+    out += lit;
     if (ip == ip_end) break;  // the last sequence carries literals only
     if (ip_end - ip < 2) return kTruncated;
-    const int64_t offset = (int64_t)ip[0] | ((int64_t)ip[1] << 8);
+    const uint32_t offset = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
     ip += 2;
-    int64_t mlen = token & 15;
+    uint32_t mlen = token & 15;
     if (mlen == 15) {
       uint32_t b;
       do {
@@ -237,15 +254,27 @@ SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *
       } while (b == 255);
     }
     mlen += 4;
-    if (offset == 0 || offset > op - window) return kBadOffset;
-    if (mlen > dst_cap - op) return kOverflow;
-    SBMC_LZ4_PUBLISH();  // the literals just written may be the match source
-    match_lanes(dst + op, offset, mlen);
-    op += mlen;
-    SBMC_LZ4_PUBLISH();
+    if (offset == 0 || (int64_t)offset > out - win) return kBadOffset;
+    if ((int64_t)mlen > out_end - out) return kOverflow;
+    SBMC_LZ4_PUBLISH();  // earlier output (incl. the literals just written) may be the source
+    if (mlen <= 32) {
+      const uint8_t *from = out - offset;
+      if (offset >= mlen) {
+        SBMC_LZ4_LANES(lane) {
+          if ((uint32_t)lane < mlen) out[lane] = from[lane];
+        }
+      } else {  // overlapping: periodic with period `offset`, every read lies below `out`
+        SBMC_LZ4_LANES(lane) {
+          if ((uint32_t)lane < mlen) out[lane] = from[(uint32_t)lane % offset];
+        }
+      }
+    } else {
+      match_lanes(out, offset, mlen);
+    }
+    out += mlen;
   }
   SBMC_LZ4_PUBLISH();
-  *op_io = op;
+  *op_io = out - dst;
   return kOk;
 }
 

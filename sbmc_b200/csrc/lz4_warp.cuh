@@ -211,13 +211,48 @@ SBMC_LZ4_FN void match_lanes(uint8_t *dst, int64_t offset, int64_t n) {
 // where most matches are one repeated float -- therefore take a loop-free path: one
 // predicated byte per lane for the literals, one for the match, 32-bit lengths, cursors as
 // pointers.  One __syncwarp() per sequence, in front of the match (it publishes the
-// previous match and this sequence's literals to the lanes that may read them).
+// previous match and this sequence's literals to the lanes that may read them).  Sequences
+// without extension bytes run in a loop whose truncation / overflow checks are hoisted.
 SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *dst,
                              int64_t *op_io, int64_t dst_cap, int64_t window) {
   uint8_t *out = dst + *op_io;
   uint8_t *const out_end = dst + dst_cap;
   const uint8_t *const win = dst + window;
+  // bytes a match may reach back from `out`, saturated (offsets are at most 65535)
+  uint32_t have = (out - win) > 0x100000 ? 0x100000u : (uint32_t)(out - win);
   for (;;) {
+    // Fast loop: sequences without length-extension bytes (at most 14 literals, a match of
+    // at most 18 bytes), while 32 input bytes and 32 output bytes are left -- no truncation
+    // / overflow checks per sequence, and such a sequence cannot be the block's last one.
+    while (ip_end - ip >= 32 && out_end - out >= 32) {
+      const uint32_t token = *ip;
+      const uint32_t lit = token >> 4, mcode = token & 15;
+      if (lit == 15 || mcode == 15) break;
+      SBMC_LZ4_LANES(lane) {
+        if ((uint32_t)lane < lit) out[lane] = ip[1 + lane];
+      }
+      const uint8_t *q = ip + 1 + lit;
+      const uint32_t offset = (uint32_t)q[0] | ((uint32_t)q[1] << 8);
+      const uint32_t mlen = mcode + 4;
+      out += lit;
+      have += lit;
+      if (offset == 0 || offset > have) return kBadOffset;
+      SBMC_LZ4_PUBLISH();  // earlier output (incl. the literals just written) may be the source
+      const uint8_t *from = out - offset;
+      if (offset >= mlen) {
+        SBMC_LZ4_LANES(lane) {
+          if ((uint32_t)lane < mlen) out[lane] = from[lane];
+        }
+      } else {  // overlapping: periodic with period `offset`, every read lies below `out`
+        SBMC_LZ4_LANES(lane) {
+          if ((uint32_t)lane < mlen) out[lane] = from[(uint32_t)lane % offset];
+        }
+      }
+      out += mlen;
+      have = have > 0x100000 ? have : have + mlen;
+      ip = q + 2;
+    }
+    // General form: one sequence with every check.
     if (ip >= ip_end) return kTruncated;
     const uint32_t token = *ip++;
     uint32_t lit = token >> 4;
@@ -240,6 +275,7 @@ SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *
     }
     ip += lit;
     out += lit;
+    have = have > 0x100000 ? have : have + (lit > 0x100000 ? 0x100000u : lit);
     if (ip == ip_end) break;  // the last sequence carries literals only
     if (ip_end - ip < 2) return kTruncated;
     const uint32_t offset = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
@@ -254,16 +290,16 @@ SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *
       } while (b == 255);
     }
     mlen += 4;
-    if (offset == 0 || (int64_t)offset > out - win) return kBadOffset;
+    if (offset == 0 || offset > have) return kBadOffset;
     if ((int64_t)mlen > out_end - out) return kOverflow;
-    SBMC_LZ4_PUBLISH();  // earlier output (incl. the literals just written) may be the source
+    SBMC_LZ4_PUBLISH();
     if (mlen <= 32) {
       const uint8_t *from = out - offset;
       if (offset >= mlen) {
         SBMC_LZ4_LANES(lane) {
           if ((uint32_t)lane < mlen) out[lane] = from[lane];
         }
-      } else {  // overlapping: periodic with period `offset`, every read lies below `out`
+      } else {
         SBMC_LZ4_LANES(lane) {
           if ((uint32_t)lane < mlen) out[lane] = from[(uint32_t)lane % offset];
         }
@@ -272,6 +308,7 @@ SBMC_LZ4_FN int decode_block(const uint8_t *ip, const uint8_t *ip_end, uint8_t *
       match_lanes(out, offset, mlen);
     }
     out += mlen;
+    have = have > 0x100000 ? have : have + (mlen > 0x100000 ? 0x100000u : mlen);
   }
   SBMC_LZ4_PUBLISH();
   *op_io = out - dst;

@@ -31,8 +31,8 @@ def main():
     ap.add_argument("--ts", type=int, default=128)
     ap.add_argument("--spp", type=int, default=8)
     ap.add_argument("--bs", type=int, default=8)
-    ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--repeat", type=int, default=8, help="times every tile appears in an epoch")
+    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--repeat", type=int, default=56, help="times every tile appears in an epoch")
     ap.add_argument("--prefetch", type=int, default=None,
                     help="PrefetchLoader device_prefetch (batches decoded ahead on a side stream)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph")
@@ -65,26 +65,32 @@ def main():
         iface = interfaces.SampleBasedDenoiserInterface(net, lr=1e-4, cuda=True, fused_optimizer=True,
                                                         cuda_graph=not a.eager)
 
-        def epochs(fn, steps):
-            """Runs fn(batch) over `steps` batches (as many epochs as it takes) -> seconds."""
+        def epochs(fn, steps, skip=0):
+            """Runs fn(batch) over skip + steps batches of ONE pass of the loader (its steady
+            state: the first `skip` batches, while the prefetch pipeline fills, are not
+            timed) -> seconds for the `steps` batches."""
             done = 0
+            t0 = None
+            for batch in loader():
+                if done == skip:
+                    th.cuda.synchronize()
+                    t0 = time.perf_counter()
+                fn(batch)
+                done += 1
+                if done >= skip + steps:
+                    break
             th.cuda.synchronize()
-            t0 = time.perf_counter()
-            while done < steps:
-                for batch in loader():
-                    fn(batch)
-                    done += 1
-                    if done >= steps:
-                        break
-            th.cuda.synchronize()
+            assert done == skip + steps, "epoch too short: raise --repeat"
             return time.perf_counter() - t0
 
         keep = {}
 
         def remember(batch):
             keep["batch"] = batch
+        skip = max(4 * (a.prefetch or 1), 16)   # the pipeline is ahead after ~3 groups (first-touch
+        #                                          allocations of the staging / decode buffers)
         epochs(remember, 8)                                   # page cache, allocator, staging
-        t_load = epochs(remember, a.steps) / a.steps
+        t_load = epochs(remember, a.steps, skip) / a.steps
         resident = {k: (v.clone() if isinstance(v, th.Tensor) else v) for k, v in keep["batch"].items()}
         for _ in range(3):
             iface.train_step(dict(resident))                  # capture / warm-up
@@ -94,8 +100,7 @@ def main():
             iface.train_step(dict(resident))
         th.cuda.synchronize()
         t_step = (time.perf_counter() - t0) / a.steps
-        epochs(lambda b: iface.train_step(b), 8)
-        t_e2e = epochs(lambda b: iface.train_step(b), a.steps) / a.steps
+        t_e2e = epochs(lambda b: iface.train_step(b), a.steps, skip) / a.steps
         samples = a.bs * a.spp * a.ts * a.ts
         print(json.dumps({
             "metric": "Msamples/s (B*spp*H*W) training end to end: tiles on disk -> optimizer step",

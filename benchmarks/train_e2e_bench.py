@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--repeat", type=int, default=56, help="times every tile appears in an epoch")
     ap.add_argument("--prefetch", type=int, default=None,
                     help="PrefetchLoader device_prefetch (batches decoded ahead on a side stream)")
+    ap.add_argument("--own_stream", action="store_true",
+                    help="run the training loop on a non-default CUDA stream")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph")
     ap.add_argument("--fp32", action="store_true", help="the reference-arithmetic fp32 path")
     ap.add_argument("--quantize", type=float, default=1.0 / 256)
@@ -59,6 +61,8 @@ def main():
         def loader():
             return datasets.PrefetchLoader(data, batch_size=a.bs, shuffle=True, drop_last=True, **kw)
 
+        if a.own_stream:
+            th.cuda.set_stream(th.cuda.Stream(device=dev))
         th.manual_seed(0)
         net = models.Multisteps(data.num_features, data.num_global_features).to(dev).train()
         net.bf16_train = not a.fp32
@@ -109,7 +113,7 @@ def main():
                                        a.bs, a.spp, a.ts, a.ts, len(files), file_bytes / 1e6),
                        "path": ("fp32 reference arithmetic" if a.fp32 else "bf16 pipeline")
                        + (", eager" if a.eager else ", one CUDA graph"),
-                       "device_prefetch": a.prefetch},
+                       "device_prefetch": a.prefetch, "own_stream": a.own_stream},
             "loader_only_ms_per_batch": 1e3 * t_load,
             "step_only_ms": 1e3 * t_step,
             "end_to_end_ms_per_step": 1e3 * t_e2e,

@@ -292,9 +292,10 @@ def test_kpcn_mode_scripts(tmp_path, backend):
 
 @pytest.mark.gpu
 def test_train_script_mixed_precision_pipeline_under_a_cuda_graph(tmp_path):
-    """scripts/train.py --bf16_train --cuda_graph: the tcgen05 training pipeline
-    (sbmc_b200/train_pipeline.py) replayed from one CUDA graph per batch shape, from the
-    .bin tiles to the checkpoint; the denoise script then loads what it wrote."""
+    """scripts/train.py --bf16_train --cuda_graph --device_prefetch 2: the tcgen05 training
+    pipeline (sbmc_b200/train_pipeline.py) replayed from one CUDA graph per batch shape while
+    the loader's worker thread decodes the next groups of batches on its side stream, from
+    the .bin tiles to the checkpoint; the denoise script then loads what it wrote."""
     import torch as th
     root = _scene(tmp_path)
     train = load_script("train")
@@ -303,7 +304,7 @@ def test_train_script_mixed_precision_pipeline_under_a_cuda_graph(tmp_path):
     train.main(train.parser().parse_args(
         ["--data", root, "--checkpoint_dir", ckpt, "--constant_spp", "--spp", "2", "--bs", "3",
          "--ksize", "3", "--num_epochs", "2", "--max_steps", "5", "--log_every", "1",
-         "--bf16_train", "--cuda_graph"]))
+         "--bf16_train", "--cuda_graph", "--device_prefetch", "2"]))
     state = th.load(os.path.join(ckpt, "training_end.pth"), map_location="cpu", weights_only=False)
     tensors = [v for v in state["model"].values() if isinstance(v, th.Tensor)]
     assert tensors and all(th.isfinite(v).all() for v in tensors)

@@ -63,6 +63,8 @@ def parse_args():
     p.add_argument("--k", type=int, default=21)
     p.add_argument("--c", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    p.add_argument("--no-train-e2e", dest="no_train_e2e", action="store_true",
+                   help="skip the end-to-end training line of the secondary block")
     p.add_argument("--no-secondary", action="store_true",
                    help="skip the configs 3 / 4 / 5 block (callers of the hot path)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -555,6 +557,25 @@ def run_secondary(a, th, dist, dev, rank, world):
             th.cuda.empty_cache()
     except Exception as exc:                      # the headline line must still be printed
         sec["error_config34"] = "%s: %s" % (type(exc).__name__, exc)
+    try:
+        if rank == 0 and not getattr(a, "no_train_e2e", False):
+            # config 4 END TO END through the callers' own loop: 128 x 128 x 8 spp tiles on disk
+            # (the renderer's .bin + LZ4 format, synthetic content) -> PrefetchLoader (GPU inflate
+            # + assembly, 16 batches decoded per launch on a side stream) -> training step
+            import contextlib
+            import io
+            from benchmarks import train_e2e_bench
+            with contextlib.redirect_stdout(io.StringIO()):
+                line = train_e2e_bench.main(["--prefetch", "16", "--tiles", "5", "--repeat", "48",
+                                             "--steps", "64"])
+            sec["config4_train_end_to_end"] = {
+                k: line[k] for k in ("end_to_end_ms_per_step", "end_to_end_Msamples_per_s",
+                                     "loader_only_ms_per_batch", "step_only_ms")}
+            sec["config4_train_end_to_end"]["workload"] = line["config"]["workload"] + "; " + \
+                line["config"]["path"] + "; device_prefetch 16; steady state of one epoch"
+            th.cuda.empty_cache()
+    except Exception as exc:
+        sec["error_config4_e2e"] = "%s: %s" % (type(exc).__name__, exc)
     try:
         if world > 1:
             # config 5: tiled inference of one 3840x2160 spp=8 frame, one row band per rank,

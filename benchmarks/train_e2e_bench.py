@@ -25,7 +25,8 @@ from sbmc_b200 import datasets, interfaces, models
 from tests import tile_io
 
 
-def main():
+def main(argv=None):
+    """Prints (and returns) the JSON line; `argv` as on the command line."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiles", type=int, default=6, help="tiles per side of the synthetic scene")
     ap.add_argument("--ts", type=int, default=128)
@@ -40,8 +41,9 @@ def main():
     ap.add_argument("--eager", action="store_true", help="no CUDA graph")
     ap.add_argument("--fp32", action="store_true", help="the reference-arithmetic fp32 path")
     ap.add_argument("--quantize", type=float, default=1.0 / 256)
-    a = ap.parse_args()
-    dev = th.device("cuda", 0)
+    a = ap.parse_args(argv)
+    dev = th.device("cuda", th.cuda.current_device())
+    line = None
     root = tempfile.mkdtemp(prefix="sbmc_train_e2e_")
     try:
         rng = np.random.default_rng(0)
@@ -106,7 +108,7 @@ def main():
         t_step = (time.perf_counter() - t0) / a.steps
         t_e2e = epochs(lambda b: iface.train_step(b), a.steps, skip) / a.steps
         samples = a.bs * a.spp * a.ts * a.ts
-        print(json.dumps({
+        line = {
             "metric": "Msamples/s (B*spp*H*W) training end to end: tiles on disk -> optimizer step",
             "config": {"workload": "BASELINE config 4 through the loader: B=%d, spp=%d, %dx%d tiles, K=21, "
                                    "%d tiles on disk (%.1f MB, LZ4 frames)" % (
@@ -119,10 +121,12 @@ def main():
             "end_to_end_ms_per_step": 1e3 * t_e2e,
             "end_to_end_Msamples_per_s": samples / t_e2e / 1e6,
             "step_only_Msamples_per_s": samples / t_step / 1e6,
-            "loader_only_Msamples_per_s": samples / t_load / 1e6}), flush=True)
+            "loader_only_Msamples_per_s": samples / t_load / 1e6}
+        print(json.dumps(line), flush=True)
         iface.close()
     finally:
         shutil.rmtree(root, ignore_errors=True)
+    return line
 
 
 if __name__ == "__main__":

@@ -230,8 +230,11 @@ class SampleBasedDenoiserInterface(object):
             self._graphs.clear()          # the optimizer's state tensors were replaced
             step = None
         if step is None:
-            if len(self._graphs) >= 4:
-                self._graphs.clear()
+            # one graph per batch signature: randomised sample counts (2 .. 8 spp) and a short
+            # last batch of an epoch all stay resident; beyond that the oldest goes
+            if len(self._graphs) >= 16:
+                oldest = next(iter(self._graphs))
+                self._graphs.pop(oldest).graph = None
             step = self._graphs[key] = _GraphedStep(self, batch)
         return step.run(batch)
 

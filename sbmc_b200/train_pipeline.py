@@ -46,7 +46,6 @@ __all__ = ["supported", "forward_train", "EmbedStage", "RegressStage", "UNetStag
            "chain_specs", "unet_specs", "embed_stage", "regress_stage", "unet_stage"]
 
 BF = th.bfloat16
-_ACT = {th.nn.ReLU: 1, th.nn.LeakyReLU: 2}
 
 
 # -- the weight bank of a model ---------------------------------------------------------------
@@ -71,9 +70,10 @@ def unet_specs(autoencoder):
     return plan, [(conv, 0, 0) for left, right in plan for conv, _ in left + (right or [])]
 
 
-def _model_bank(model, nf, ngf):
+def _model_bank(model):
     """(bank, index) of a Multisteps model; cached on the model, rebuilt when a parameter
-    moved.  index: {"embed": [(k1, k2, k3)], "unet": [(plan, [k...])], "reg": (k1, k2, k3)}."""
+    moved.  Layer 1 of the first embedding sees the nf + ngf <= 128 input channels padded to
+    128, every later chain 128 sample + 128 pixel channels.  index: {"embed": [(k1, k2, k3)], "unet": [(plan, [k...])], "reg": (k1, k2, k3)}."""
     specs, index = [], {"embed": [], "unet": []}
     for step in range(model.nsteps):
         k = len(specs)
@@ -393,7 +393,7 @@ def forward_train(model, radiance, features, gfeatures):
     gidx = th.arange(bs * spp, device=feats.device) % bs
     x[:, :, nf:nf + ngf] = gfeatures.reshape(bs, ngf)[gidx].unsqueeze(1).to(BF)
     x = x.view(bs * spp * hw, 128)
-    bank, index = _model_bank(model, nf, ngf)
+    bank, index = _model_bank(model)
     toks = bank.apply()                      # one launch: every bf16 operand of the step
     prop = None
     for step in range(model.nsteps):
